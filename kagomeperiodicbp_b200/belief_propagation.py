@@ -1,0 +1,393 @@
+"""Block belief propagation on the periodic Kagome block -- the accelerated counterpart of
+src/algo/belief_propagation.py with the same entry points:
+
+    belief_propagation(tn, messages, config)          (reference :192-281)
+    robust_belief_propagation(tn, messages, config)   (reference :285-350)
+
+One BP iteration computes the six outgoing block messages Jacobi-style from the same incoming set
+(reference :120-161).  Here each of the six chains is ONE device program that runs, without leaving the
+GPU: the boundary-MPS contraction towards its side (``contract_tensor_network`` -> ``bubblecon``), the
+normalisation ``_fix_messages`` (:113-117), the overlap with the previous message that ``_compute_error``
+needs (:44-56), and the damping ``_single_mps_damping`` (:59-74).  The six programs run concurrently on six
+CUDA streams; the host only relabels sides (periodic boundary, :155), averages six numbers into the error
+and applies the reference's convergence / failure / retry logic.
+"""
+from __future__ import annotations
+
+import copy
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import block_tn, contraction_order
+from .containers import BPConfig, BPStats, Message, MPSOrientation, UnitCell
+from .dev_bubblecon import trace_bubblecon
+from .dev_mps import SLOT_LOGNORM, SLOT_NONFINITE, SLOT_TRUNC, DevMPS, add_two_mps, inner_product
+from .engine import E_SVD_NOCONV, BubbleConError
+from .lattice import BLOCK_SIDES_CCW, SIDE_ANGLE, SIDE_OPPOSITE, get_block
+from .mps import MPS
+from .program import Program
+from .runtime import Compiled, get_engine
+
+SLOT_IP_RE, SLOT_IP_IM = 3, 4
+SLOT_TRUNC_DAMP = 5
+N_SLOTS = 8
+
+_pool = ThreadPoolExecutor(max_workers=6, thread_name_prefix="kbp-side")
+_cache: dict = {}
+
+
+# ------------------------------------------------------------------------------------------------
+# the tensor network container (API of KagomeTNRepeatedUnitCell, src/tensor_networks/tensor_network.py:335)
+# ------------------------------------------------------------------------------------------------
+class KagomeTNRepeatedUnitCell:
+    def __init__(self, unit_cell: UnitCell, N: int, d: int | None = None, D: int | None = None):
+        self.unit_cell = unit_cell
+        self.N = N
+        self.lattice = get_block(N)
+        self.d = unit_cell.A.shape[0] if d is None else d
+        self.D = unit_cell.A.shape[1] if D is None else D
+        self.messages: dict = {}
+
+    @property
+    def num_message_connections(self) -> int:
+        return self.lattice.L
+
+    @property
+    def has_messages(self) -> bool:
+        return len(self.messages) == 6
+
+    def connect_messages(self, messages: dict):
+        for side, m in messages.items():
+            self.messages[side] = m
+
+    def connect_uniform_messages(self):
+        self.connect_messages(initial_messages(self.D, self.N, "UQ"))
+
+    def connect_random_messages(self, rng=None):
+        self.connect_messages(initial_messages(self.D, self.N, "RQ", rng))
+
+    def message_indices(self, side: str):
+        return self.lattice.message_indices(side)
+
+
+def kagome_tn_from_unit_cell(unit_cell: UnitCell, dims) -> KagomeTNRepeatedUnitCell:
+    """(src/tensor_networks/construction.py:45-52)"""
+    return KagomeTNRepeatedUnitCell(unit_cell, dims.big_lattice_size, dims.physical_dim, dims.virtual_dim)
+
+
+# ------------------------------------------------------------------------------------------------
+# initial messages (src/tensor_networks/mps.py:77-180): product of vectorised identities (UQ) or random
+# |v><v| (RQ) embedded with bond D^2, left-canonicalised on the device
+# ------------------------------------------------------------------------------------------------
+def _raw_initial_sites(D: int, L: int, random: bool, rng):
+    D2, D3 = D * D, D ** 3
+    sites = []
+    for i in range(L):
+        if random:
+            rs = np.random if rng is None else rng
+            a = rs.normal(size=[D3, D3]) + 1j * rs.normal(size=[D3, D3])
+            a /= np.linalg.norm(a)
+            kb = a @ np.conj(a.T)
+        else:
+            kb = np.eye(D3) / np.sqrt(D3)
+        kb = kb.reshape([D] * 6).transpose([0, 3, 1, 4, 2, 5]).reshape([D2, D2, D2])
+        if i == 0:
+            kb = kb[0, :, :].reshape([1, D2, D2])
+        if i == L - 1:
+            kb = kb[:, :, 0].reshape([kb.shape[0], D2, 1])
+        sites.append(np.ascontiguousarray(kb, dtype=np.complex128))
+    return sites
+
+
+def _canonicalize_program(shapes):
+    key = ("canon", tuple(shapes))
+    if key not in _cache:
+        p = Program(N_SLOTS)
+        ins = [(f"s{k}", p.input(f"s{k}", sh)) for k, sh in enumerate(shapes)]
+        mp = DevMPS(p, len(shapes))
+        for k, (_, t) in enumerate(ins):
+            mp.set_site(t, k)
+        mp.left_canonical_QR()
+        last = p.copy(mp.A[-1])
+        p.normalize_(last, SLOT_LOGNORM)
+        mp.A[-1] = last
+        _cache[key] = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mp.A)])
+    return _cache[key]
+
+
+def initial_message(D: int, N: int, message_model: str = "RQ", rng=None) -> MPS:
+    """``N`` = number of MPS sites (= 2*block_size - 1), as in the reference's signature."""
+    raw = _raw_initial_sites(D, N, message_model in ("RQ", "RANDOM_QUANTUM"), rng)
+    comp = _canonicalize_program([s.shape for s in raw])
+    outs, _, _ = comp.run(get_engine("setup"), [{f"s{k}": s for k, s in enumerate(raw)}])
+    m = MPS.from_sites([outs[0][f"o{k}"] for k in range(N)], Corder=["L"] * (N - 1) + [None])
+    return m
+
+
+def initial_messages(D: int, block_N: int, model: str = "UQ", rng=None) -> dict:
+    L = 2 * block_N - 1
+    out = {}
+    for side in BLOCK_SIDES_CCW:
+        out[side] = Message(initial_message(D, L, model, rng), MPSOrientation.standard(SIDE_OPPOSITE[side]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# one chain = one program
+# ------------------------------------------------------------------------------------------------
+def _msg_shapes(messages: dict):
+    return tuple(tuple(tuple(a.shape) for a in messages[s].mps.A) for s in BLOCK_SIDES_CCW)
+
+
+def _node_tensor(k: int, L: int, t):
+    """message site k as the 2- or 3-leg node the TN uses (src/tensor_networks/tensor_network.py:855-870)."""
+    if k == 0:
+        return t.reshape(t.shape[1], t.shape[2])
+    if k == L - 1:
+        return t.reshape(t.shape[0], t.shape[1])
+    return t
+
+
+def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes, damping, depth="ToMessage",
+                         epilogue=True) -> Compiled:
+    key = ("side", N, d, D, side, chi, msg_shapes, damping, depth, epilogue)
+    if key in _cache:
+        return _cache[key]
+    blk = get_block(N)
+    L = blk.L
+    p = Program(N_SLOTS)
+    ins = []
+    cell_dt = []
+    for nm in "ABC":
+        t = p.input(f"cell{nm}", (d, D, D, D, D))
+        ins.append((f"cell{nm}", t))
+        cell_dt.append(t)
+    used = [s for s in BLOCK_SIDES_CCW if s != side] if depth == "ToMessage" else list(BLOCK_SIDES_CCW)
+    msg_dt = {}
+    for si, s in enumerate(BLOCK_SIDES_CCW):
+        if s not in used:
+            continue
+        msg_dt[s] = []
+        for k, sh in enumerate(msg_shapes[si]):
+            t = p.input(f"m{s}{k}", sh)
+            ins.append((f"m{s}{k}", t))
+            msg_dt[s].append(t)
+    # TN description with shape-only placeholders, then swap in device tensors
+    dummy_cell = [np.empty((d, D, D, D, D))] * 3
+    dummy_msgs = {s: [np.empty(sh) for sh in msg_shapes[si]] for si, s in enumerate(BLOCK_SIDES_CCW)}
+    T, E, A, K, P = block_tn.assemble(N, dummy_cell, dummy_msgs)
+    T, E, A = block_tn.connect_corner(N, T, E, A, P, side)
+    TL = [None] * len(T)
+    for s_ in blk.sites:
+        TL[s_.index] = cell_dt[s_.index % 3]
+    for s in BLOCK_SIDES_CCW:
+        for k, idx in enumerate(blk.message_indices(s)):
+            if s in msg_dt:
+                TL[idx] = _node_tensor(k, L, msg_dt[s][k]).reshape(T[idx].shape)
+    order = list(contraction_order.kagome_order(N, side, depth))
+    mp, _ = trace_bubblecon(p, TL, E, A, SIDE_ANGLE[side], order, chi, ket_tensors=K, slots=(SLOT_LOGNORM, SLOT_TRUNC))
+    outs = []
+    if epilogue:
+        opp = SIDE_OPPOSITE[side]
+        # _fix_messages: right-canonical + unit norm (reference :113-117)
+        mp.right_canonical(nr_bulk=True)
+        for k, t in enumerate(mp.A):
+            outs.append((f"out{k}", t))
+            p.nonfinite(t, SLOT_NONFINITE)
+        prev = DevMPS(p, L)
+        for k, t in enumerate(msg_dt[opp]):
+            prev.set_site(t, k)
+        ip = inner_product(p, prev, mp)                       # <prev|out>
+        p.scalar_to_slot(ip, SLOT_IP_RE, SLOT_IP_IM)
+        if damping:
+            comb = add_two_mps(p, mp, 1.0 - damping, prev, damping, sign_slot_beta=SLOT_IP_RE)
+            comb.slot_lognorm, comb.slot_trunc = SLOT_LOGNORM, SLOT_TRUNC_DAMP
+            comb.left_canonical_QR()
+            comb.right_canonical(maxD=chi, nr_bulk=True)
+            for k, t in enumerate(comb.A):
+                outs.append((f"next{k}", t))
+    else:
+        for k, t in enumerate(mp.A):
+            outs.append((f"out{k}", t))
+    comp = Compiled(p, ins, outs, meta=dict(n_out=mp.N, L=L, side=side, svd_shapes=list(p.svd_shapes),
+                                            qr_shapes=list(p.qr_shapes), gemm_flops=p.gemm_flops))
+    _cache[key] = comp
+    return comp
+
+
+def _side_inputs(cell: UnitCell, messages: dict, comp: Compiled) -> dict:
+    d = {"cellA": cell.A, "cellB": cell.B, "cellC": cell.C}
+    names = {n for n, _, _ in comp.in_layout}
+    for s in BLOCK_SIDES_CCW:
+        for k, a in enumerate(messages[s].mps.A):
+            nm = f"m{s}{k}"
+            if nm in names:
+                d[nm] = a
+    return d
+
+
+def _run_side(side: str, comp: Compiled, batch_inputs: list, device: int):
+    eng = get_engine(("side", side), device)
+    outs, slots, rc = comp.run(eng, batch_inputs, soft_errors=(E_SVD_NOCONV,))
+    return side, outs, slots, rc
+
+
+def bp_step_batch(N: int, cells: list, messages_list: list, config: BPConfig, device: int = 0):
+    """one BP iteration for a batch of independent unit cells that share all shapes.  Returns per cell
+    (out_messages, next_messages, error, trunc_error)."""
+    d, D = cells[0].A.shape[0], cells[0].A.shape[1]
+    shapes = _msg_shapes(messages_list[0])
+    for m in messages_list[1:]:
+        assert _msg_shapes(m) == shapes, "batched cells must share message shapes"
+    damping = config.damping if config.damping else None
+    futs = []
+    for side in BLOCK_SIDES_CCW:
+        comp = compile_side_program(N, d, D, side, config.trunc_dim, shapes, damping)
+        batch = [_side_inputs(c, m, comp) for c, m in zip(cells, messages_list)]
+        futs.append(_pool.submit(_run_side, side, comp, batch, device))
+    res = {}
+    for f in futs:
+        side, outs, slots, rc = f.result()
+        res[side] = (outs, slots, rc)
+    L = 2 * N - 1
+    results = []
+    for ci in range(len(cells)):
+        out_msgs, next_msgs, dists, trunc = {}, {}, [], 0.0
+        for side in BLOCK_SIDES_CCW:
+            outs, slots, rc = res[side]
+            if slots[ci, SLOT_NONFINITE] > 0:
+                raise BubbleConError(f"non-finite values in the outgoing message towards {side}")
+            opp = SIDE_OPPOSITE[side]
+            o = outs[ci]
+            n_out = sum(1 for k in o if k.startswith("out"))
+            orient = MPSOrientation.standard(side)
+            out_mps = MPS.from_sites([o[f"out{k}"] for k in range(n_out)], Corder=[None] + ["R"] * (n_out - 1))
+            out_msgs[opp] = Message(out_mps, orient)
+            if damping:
+                nx = MPS.from_sites([o[f"next{k}"] for k in range(n_out)], Corder=[None] + ["R"] * (n_out - 1))
+                next_msgs[opp] = Message(nx, orient)
+            ip = complex(slots[ci, SLOT_IP_RE], slots[ci, SLOT_IP_IM])
+            dist = 1.0 - abs(ip)
+            dists.append(0.0 if dist < 0 else dist)
+            trunc += float(slots[ci, SLOT_TRUNC])
+        if config.msg_diff_squared:
+            err = sum(dists) / len(dists)
+        else:
+            err = float(np.sqrt(sum(dists)) / len(dists))
+        results.append((out_msgs, next_msgs if damping else out_msgs, float(err), trunc))
+    return results
+
+
+def _belief_propagation_step(tn: KagomeTNRepeatedUnitCell, prev_messages: dict, prev_error, config: BPConfig, prog_bar_obj=None):
+    """(reference :164-188) -> (out_messages, next_messages, next_error)"""
+    out, nxt, err, _ = bp_step_batch(tn.N, [tn.unit_cell], [prev_messages], config)[0]
+    return out, nxt, err
+
+
+# ------------------------------------------------------------------------------------------------
+# hermitisation at the end of BP (src/libs/ITE.py:116-185)
+# ------------------------------------------------------------------------------------------------
+def _hermitize_program(shapes) -> Compiled:
+    key = ("herm", tuple(shapes))
+    if key in _cache:
+        return _cache[key]
+    p = Program(N_SLOTS)
+    ins = [(f"s{k}", p.input(f"s{k}", sh)) for k, sh in enumerate(shapes)]
+    N = len(shapes)
+    mpA, mpB = DevMPS(p, N), DevMPS(p, N)
+    Dmax = 0
+    for k, (_, t) in enumerate(ins):
+        DL, d2, DR = t.shape
+        dd = int(round(np.sqrt(d2)))
+        mpA.set_site(t, k)
+        tb = p.transpose(t.reshape(DL, dd, dd, DR), (0, 2, 1, 3), conj=True).reshape(DL, d2, DR)
+        mpB.set_site(tb, k)
+        Dmax = max(Dmax, DL)
+    mpC = add_two_mps(p, mpA, 0.5, mpB, 0.5)
+    mpC.reduceD(Dmax)
+    comp = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mpC.A)])
+    _cache[key] = comp
+    return comp
+
+
+def _hermitize_messages(messages: dict) -> dict:
+    def one(side):
+        m = messages[side]
+        comp = _hermitize_program([a.shape for a in m.mps.A])
+        outs, _, _ = comp.run(get_engine(("side", side)), [{f"s{k}": a for k, a in enumerate(m.mps.A)}],
+                              soft_errors=(E_SVD_NOCONV,))
+        o = outs[0]
+        return side, Message(MPS.from_sites([o[f"o{k}"] for k in range(m.mps.N)]), m.orientation)
+    return dict(_pool.map(one, list(messages.keys())))
+
+
+# ------------------------------------------------------------------------------------------------
+def belief_propagation(tn: KagomeTNRepeatedUnitCell, messages: dict | None = None, config: BPConfig = None):
+    """(reference :192-281)  -> (messages, BPStats)"""
+    config = BPConfig() if config is None else config
+    t0 = time.perf_counter()
+    if messages is None:
+        tn.connect_random_messages() if config.init_msg in ("RQ", "RANDOM_QUANTUM") else tn.connect_uniform_messages()
+    else:
+        tn.connect_messages(messages)
+    messages = tn.messages
+    errors, trunc_errs = [], []
+    min_error, min_messages = np.inf, messages
+    next_messages = out_messages = messages
+    error, success, i = None, False, 0
+    it = 0
+    while config.max_iterations is None or it < config.max_iterations:
+        i = it
+        out_messages, next_messages, error, trunc = bp_step_batch(tn.N, [tn.unit_cell], [next_messages], config)[0]
+        trunc_errs.append(trunc)
+        it += 1
+        if error < config.msg_diff_terminate:
+            success = True
+            errors.append(error)
+            break
+        tn.connect_messages(next_messages)
+        if error < min_error:
+            min_error, min_messages = error, copy.deepcopy(out_messages)
+        errors.append(error)
+        k = config.times_to_deem_failure_when_diff_increases
+        if len(errors) > k and all(a <= b for a, b in zip(errors[-k:], errors[-k:][1:])):
+            break
+    assert isinstance(error, float)
+    if not success:
+        out_messages, error = min_messages, min_error
+    if config.hermitize_msgs_when_finished:
+        out_messages = _hermitize_messages(out_messages)
+    tn.connect_messages(out_messages)
+    stats = BPStats(iterations=i + 1, final_error=float(error), final_config=config, success=success,
+                    execution_time=time.perf_counter() - t0, errors=errors, truncation_errors=trunc_errs)
+    return out_messages, stats
+
+
+def robust_belief_propagation(tn: KagomeTNRepeatedUnitCell, messages: dict | None = None, config: BPConfig = None):
+    """(reference :285-350)"""
+    config = (BPConfig() if config is None else config).copy()
+    t0 = time.perf_counter()
+    messages_in = copy.deepcopy(messages)
+    min_messages, min_error, total_iterations = messages_in, np.inf, 0
+    messages_out = error_out = None
+    attempt_ind, stats = 0, None
+    for attempt_ind in range(config.allowed_retries):
+        msgs, stats = belief_propagation(tn, messages_in, config)
+        total_iterations += stats.iterations
+        if stats.final_error < config.msg_diff_terminate:
+            messages_out, error_out = msgs, stats.final_error
+            break
+        if stats.final_error < min_error:
+            min_error, min_messages = stats.final_error, copy.deepcopy(msgs)
+        config.trunc_dim = int(1.5 * config.trunc_dim)
+        if isinstance(config.max_iterations, int):
+            config.max_iterations += 11
+        messages_in = None
+    else:
+        messages_out, error_out = min_messages, min_error
+    tn.connect_messages(messages_out)
+    return messages_out, BPStats(attempts=attempt_ind + 1, iterations=total_iterations, final_error=float(error_out),
+                                 final_config=stats.final_config, success=error_out < config.msg_diff_good_enough,
+                                 execution_time=time.perf_counter() - t0)

@@ -1,0 +1,117 @@
+// Batched complex128 Householder QR, one CTA per chain.  A(m x n, row-major) = Q(m x r) R(r x n),
+// r = min(m, n), Q with orthonormal columns even when A is rank deficient (the boundary MPS is
+// rank deficient on the first swallows of every chain, so Cholesky-type QR is not an option).
+// The matrix is worked on column-major in a scratch buffer (L2-resident: <= a few MB), one warp per
+// trailing column, lanes strided over rows, dot products reduced with warp shuffles.
+#include "kbp_common.cuh"
+#include "kbp_ops.cuh"
+
+namespace kbp {
+
+__global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ base, long long chain_stride, long long A_,
+                                                             long long Q_, long long R_, long long work_, int m, int n) {
+  __shared__ double red[34];
+  __shared__ cplx sh_inv_u0, sh_s;
+  __shared__ double sh_tau;
+  cplx* cb = base + (long long)blockIdx.x * chain_stride;
+  const cplx* A = cb + A_;
+  cplx* Q = cb + Q_;
+  cplx* R = cb + R_;
+  cplx* W = cb + work_;                        // m x n, column-major
+  const int kk = m < n ? m : n;
+  cplx* Qw = W + (long long)m * n;             // m x kk, column-major
+  double* tau = reinterpret_cast<double*>(Qw + (long long)m * kk);  // kk doubles
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, w = t >> 5, nw = nt >> 5;
+
+  for (long long i = t; i < (long long)m * n; i += nt) {
+    int r = (int)(i / n), c = (int)(i % n);
+    W[(long long)c * m + r] = A[i];
+  }
+  __syncthreads();
+
+  for (int j = 0; j < kk; ++j) {
+    cplx* x = W + (long long)j * m;
+    double sig = 0.0;
+    for (int i = j + 1 + t; i < m; i += nt) sig += cabs2(x[i]);
+    sig = block_sum(sig, red);
+    if (t == 0) {
+      cplx alpha = x[j];
+      double absa = sqrt(cabs2(alpha));
+      double nrm = sqrt(fma(absa, absa, sig));
+      if (nrm == 0.0) {
+        sh_tau = 0.0; sh_s = cmake(0.0, 0.0); sh_inv_u0 = cmake(0.0, 0.0);
+      } else {
+        cplx ph = absa > 0.0 ? cscale(alpha, 1.0 / absa) : cmake(1.0, 0.0);
+        cplx s = cscale(ph, -nrm);
+        cplx u0 = csub(alpha, s);                       // = ph * (absa + nrm): no cancellation
+        double u02 = cabs2(u0);
+        sh_tau = 2.0 * u02 / (u02 + sig);
+        sh_inv_u0 = cscale(cconj(u0), 1.0 / u02);
+        sh_s = s;
+      }
+      tau[j] = sh_tau;
+    }
+    __syncthreads();
+    const cplx inv_u0 = sh_inv_u0;
+    const double tj = sh_tau;
+    for (int i = j + 1 + t; i < m; i += nt) x[i] = cmul(x[i], inv_u0);
+    if (t == 0) x[j] = sh_s;
+    __syncthreads();
+    if (tj != 0.0) {
+      for (int c = j + 1 + w; c < n; c += nw) {
+        cplx* a = W + (long long)c * m;
+        cplx d = cmake(0.0, 0.0);
+        for (int i = j + 1 + lane; i < m; i += 32) d = cadd(d, ccmul(x[i], a[i]));
+        d = warp_sum(d);
+        d = cadd(d, a[j]);
+        d = cscale(d, tj);
+        for (int i = j + 1 + lane; i < m; i += 32) a[i] = csub(a[i], cmul(x[i], d));
+        __syncwarp();
+        if (lane == 0) a[j] = csub(a[j], d);
+      }
+    }
+    __syncthreads();
+  }
+
+  // R (kk x n, row-major): upper triangle of W
+  for (long long i = t; i < (long long)kk * n; i += nt) {
+    int r = (int)(i / n), c = (int)(i % n);
+    R[i] = r <= c ? W[(long long)c * m + r] : cmake(0.0, 0.0);
+  }
+  // Q = H_0 H_1 ... H_{kk-1} applied to the first kk columns of the identity
+  for (long long i = t; i < (long long)m * kk; i += nt) {
+    int c = (int)(i / m), r = (int)(i % m);
+    Qw[i] = r == c ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int j = kk - 1; j >= 0; --j) {
+    const cplx* v = W + (long long)j * m;
+    const double tj = tau[j];
+    if (tj != 0.0) {
+      for (int c = j + w; c < kk; c += nw) {
+        cplx* qc = Qw + (long long)c * m;
+        cplx d = cmake(0.0, 0.0);
+        for (int i = j + 1 + lane; i < m; i += 32) d = cadd(d, ccmul(v[i], qc[i]));
+        d = warp_sum(d);
+        d = cadd(d, qc[j]);
+        d = cscale(d, tj);
+        for (int i = j + 1 + lane; i < m; i += 32) qc[i] = csub(qc[i], cmul(v[i], d));
+        __syncwarp();
+        if (lane == 0) qc[j] = csub(qc[j], d);
+      }
+    }
+    __syncthreads();
+  }
+  for (long long i = t; i < (long long)m * kk; i += nt) {
+    int r = (int)(i / kk), c = (int)(i % kk);
+    Q[i] = Qw[(long long)c * m + r];
+  }
+}
+
+void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
+  if (m == 0 || n == 0) return;
+  qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n);
+  ++*a.launches;
+}
+
+}  // namespace kbp

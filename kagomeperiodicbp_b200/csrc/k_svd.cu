@@ -1,0 +1,430 @@
+// Batched truncated SVD of complex128 matrices by block one-sided Jacobi (Hestenes) -- the kernel
+// that replaces the reference's numpy.linalg.svd inside right_canonical (src/libs/bmpslib.py:733-772),
+// where >= 60 % of its wall time goes.
+//
+// Work matrix Z (p_pad x LD, row-major), rows = the vectors being orthogonalised:
+//     Z = [ X | J ],   X = A^T (m >= n, "mode T")  or  X = A (m < n, "mode N"),   J = I  (accumulates the rotations)
+// so p = min(m, n) vectors of length q = max(m, n).  Rows are grouped in blocks of 16; one sweep visits
+// all block pairs in a round-robin tournament (nblk-1 rounds of nblk/2 independent pairs, one CTA per
+// pair and chain, one launch per round).  Per pair:
+//   1. Gram  G = P P^H  (32 x 32) over the X columns                 -- DMMA (FP64 tensor pipe)
+//   2. Hermitian Jacobi eigensolve  G = W L W^H  in shared memory, eigenvalues sorted descending
+//   3. rotate the 32 rows:  P <- W^H P  over all LD columns (X and J)  -- DMMA
+// A pair whose largest |G_ij| / sqrt(G_ii G_jj) is below tol is left alone; a sweep in which every
+// pair was left alone ends the iteration (one pinned-memory flag read per sweep).  After convergence
+// the rows of X are mutually orthogonal:  A = J^H diag(s) Yhat  (mode N)  or  A = Yhat^T diag(s) conj(J)
+// (mode T), with s_i the row norms; the extraction kernel sorts s, keeps the largest `keep`, and
+// writes U_k diag(s_k) and V_k^H -- in mode T without ever dividing by a singular value.
+#include "kbp_common.cuh"
+#include "kbp_ops.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace kbp {
+
+constexpr int JB = 16;        // rows per block
+constexpr int PR = 2 * JB;    // rows per pair
+constexpr int KC = 32;        // columns staged per Gram step
+constexpr int LDP = KC + 4;   // shared row stride (doubles): 36 mod 16 == 4 -> conflict-free fragments
+constexpr size_t SVD_ROUND_SMEM = 2 * sizeof(double2) * PR * (PR + 1) + 2 * sizeof(double) * PR * LDP;
+constexpr double SVD_TOL = 1e-14;
+constexpr int SVD_MAX_SWEEPS = 40;
+
+static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct SvdGeom {
+  int mode_t;           // 1: X = A^T, 0: X = A
+  int m, n, p, q;
+  int p_pad, q_pad, ld;
+  int nblk;
+};
+
+static SvdGeom svd_geom(int64_t m, int64_t n) {
+  SvdGeom g;
+  g.m = (int)m; g.n = (int)n;
+  g.mode_t = m >= n;
+  g.p = (int)(m >= n ? n : m);
+  g.q = (int)(m >= n ? m : n);
+  g.p_pad = (int)round_up(g.p, PR);
+  g.q_pad = (int)round_up(g.q, 8);
+  g.ld = g.q_pad + g.p_pad;
+  g.nblk = g.p_pad / JB;
+  return g;
+}
+
+int64_t svd_work_elems(int64_t m, int64_t n) {
+  SvdGeom g = svd_geom(m, n);
+  return (int64_t)g.p_pad * g.ld;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void svd_init_kernel(cplx* __restrict__ base, long long chain_stride, long long A_, long long Z_, SvdGeom g) {
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const cplx* A = cb + A_;
+  cplx* Z = cb + Z_;
+  const long long total = (long long)g.p_pad * g.ld;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int i = (int)(e / g.ld), c = (int)(e % g.ld);
+    cplx v = cmake(0.0, 0.0);
+    if (c < g.q_pad) {
+      if (i < g.p && c < g.q) v = g.mode_t ? A[(long long)c * g.n + i] : A[(long long)i * g.n + c];
+    } else if (c - g.q_pad == i) {
+      v = cmake(1.0, 0.0);
+    }
+    Z[e] = v;
+  }
+}
+
+// round-robin tournament: players 0..n-1 (n even), round r in [0, n-1), table t in [0, n/2)
+__device__ __forceinline__ void rr_pair(int n, int r, int t, int& a, int& b) {
+  const int m = n - 1;
+  if (t == 0) { a = m; b = r; }
+  else { a = (r + t) % m; b = (r - t + m) % m; }
+  if (a > b) { int x = a; a = b; b = x; }
+}
+
+__device__ __forceinline__ unsigned long long dbl_bits_nonneg(double x) { return (unsigned long long)__double_as_longlong(x); }
+
+__global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base, long long chain_stride, long long Z_, SvdGeom g,
+                                                        int round, double tol, const double* __restrict__ off_prev,
+                                                        double* __restrict__ off_cur) {
+  // shared: staged operand planes (phase 1) reused as W^H planes (phase 3); G and W for the eigensolve
+  extern __shared__ __align__(16) unsigned char svd_smem[];
+  cplx (*Gs)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem);
+  cplx (*Ws)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem + sizeof(cplx) * PR * (PR + 1));
+  double (*Ps_re)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 2 * sizeof(cplx) * PR * (PR + 1));
+  double (*Ps_im)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 2 * sizeof(cplx) * PR * (PR + 1) + sizeof(double) * PR * LDP);
+  __shared__ double rot_c[JB], rot_s[JB];
+  __shared__ cplx rot_e[JB];
+  __shared__ double sh_red[34];
+  __shared__ int perm[PR];
+  __shared__ double sh_sweep_off;
+
+  const int chain = blockIdx.y;
+  if (off_prev[chain] < tol) return;            // this chain converged in the previous sweep
+  cplx* Z = base + (long long)chain * chain_stride + Z_;
+  int bi, bj;
+  rr_pair(g.nblk, round, blockIdx.x, bi, bj);
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, gq = lane >> 2, q = lane & 3;
+  const int ld = g.ld;
+  auto grow = [&](int k) -> long long { return (long long)(k < JB ? bi * JB + k : bj * JB + (k - JB)) * ld; };
+
+  // ---------------- phase 1: G = P P^H over the X columns (DMMA) ----------------
+  const int mt = w & 1, ntile = w >> 1;          // warp's 16x8 tile of the 32x32 Gram matrix
+  double gr[4] = {0, 0, 0, 0}, gi[4] = {0, 0, 0, 0};
+  cplx stage[4];
+  const int sc = t & 31, sr = t >> 5;            // staging: column sc, rows sr + 8*r
+  auto fetch = [&](int c0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int c = c0 + sc;
+      stage[r] = c < g.q_pad ? Z[grow(sr + 8 * r) + c] : cmake(0.0, 0.0);
+    }
+  };
+  fetch(0);
+  for (int c0 = 0; c0 < g.q_pad; c0 += KC) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { Ps_re[sr + 8 * r][sc] = stage[r].x; Ps_im[sr + 8 * r][sc] = stage[r].y; }
+    __syncthreads();
+    if (c0 + KC < g.q_pad) fetch(c0 + KC);
+#pragma unroll
+    for (int ks = 0; ks < KC / 8; ++ks) {
+      double ar[4], ai[4], an[4], br[2], bim[2];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int rr = mt * 16 + gq + 8 * (v & 1), kk = ks * 8 + q + 4 * (v >> 1);
+        ar[v] = Ps_re[rr][kk]; ai[v] = Ps_im[rr][kk]; an[v] = -ar[v];
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int rr = ntile * 8 + gq, kk = ks * 8 + q + 4 * v;
+        br[v] = Ps_re[rr][kk]; bim[v] = Ps_im[rr][kk];
+      }
+      // (ar + i ai)(br - i bi): re = ar br + ai bi, im = ai br - ar bi
+      dmma16x8x8(gr, ar, br);
+      dmma16x8x8(gr, ai, bim);
+      dmma16x8x8(gi, ai, br);
+      dmma16x8x8(gi, an, bim);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) Gs[mt * 16 + gq + 8 * (v >> 1)][ntile * 8 + 2 * q + (v & 1)] = cmake(gr[v], gi[v]);
+  __syncthreads();
+
+  // ---------------- convergence measure of this pair ----------------
+  double off = 0.0;
+  for (int e = t; e < PR * PR; e += 256) {
+    const int i = e / PR, j = e % PR;
+    if (i < j) {
+      const double dd = Gs[i][i].x * Gs[j][j].x;
+      if (dd > 0.0) off = fmax(off, sqrt(cabs2(Gs[i][j]) / dd));
+    }
+  }
+  off = warp_max(off);
+  if (lane == 0) sh_red[w] = off;
+  __syncthreads();
+  if (t < 32) {
+    double x = t < 8 ? sh_red[t] : 0.0;
+    x = warp_max(x);
+    if (t == 0) sh_red[33] = x;
+  }
+  __syncthreads();
+  off = sh_red[33];
+  if (t == 0) atomicMax(reinterpret_cast<unsigned long long*>(off_cur + chain), dbl_bits_nonneg(off));
+  if (off < tol) return;
+
+  // ---------------- phase 2: Hermitian Jacobi eigensolve of G (shared memory) ----------------
+  for (int e = t; e < PR * PR; e += 256) Ws[e / PR][e % PR] = (e / PR == e % PR) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+  __syncthreads();
+  for (int isweep = 0; isweep < 15; ++isweep) {
+    if (t == 0) sh_sweep_off = 0.0;
+    for (int step = 0; step < PR - 1; ++step) {
+      if (t < JB) {
+        int a, b;
+        rr_pair(PR, step, t, a, b);
+        const double gaa = Gs[a][a].x, gbb = Gs[b][b].x;
+        const cplx gab = Gs[a][b];
+        const double ab = sqrt(cabs2(gab));
+        double c = 1.0, s = 0.0;
+        cplx e = cmake(1.0, 0.0);
+        const double dd = gaa * gbb;
+        double ratio = 0.0;
+        if (ab > 0.0 && dd > 0.0) ratio = ab / sqrt(dd);
+        if (ab > 0.0 && (ratio > 1e-17 || !(dd > 0.0))) {
+          const double zeta = (gbb - gaa) / (2.0 * ab);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = tt * c;
+          e = cmake(gab.x / ab, -gab.y / ab);   // e^{-i phi}
+        }
+        rot_c[t] = c; rot_s[t] = s; rot_e[t] = e;
+        double mx = ratio;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0x0000ffffu, mx, o));
+        if (t == 0) sh_sweep_off = fmax(sh_sweep_off, mx);
+      }
+      __syncthreads();
+      // column update  M <- M R  for G and W:  512 + 512 (row, pair) tasks
+      for (int task = t; task < 2 * PR * JB; task += 256) {
+        const int which = task / (PR * JB), rem = task % (PR * JB);
+        const int row = rem / JB, k = rem % JB;
+        int a, b;
+        rr_pair(PR, step, k, a, b);
+        const double c = rot_c[k], s = rot_s[k];
+        const cplx e = rot_e[k];
+        cplx (*M)[PR + 1] = which ? Ws : Gs;
+        const cplx xa = M[row][a], xb = M[row][b];
+        const cplx eb = cmul(e, xb);
+        M[row][a] = make_double2(c * xa.x - s * eb.x, c * xa.y - s * eb.y);
+        M[row][b] = make_double2(s * xa.x + c * eb.x, s * xa.y + c * eb.y);
+      }
+      __syncthreads();
+      // row update  G <- R^H G
+      for (int task = t; task < PR * JB; task += 256) {
+        const int col = task / JB, k = task % JB;
+        int a, b;
+        rr_pair(PR, step, k, a, b);
+        const double c = rot_c[k], s = rot_s[k];
+        const cplx ec = cconj(rot_e[k]);         // e^{+i phi}
+        const cplx xa = Gs[a][col], xb = Gs[b][col];
+        const cplx eb = cmul(ec, xb);
+        Gs[a][col] = make_double2(c * xa.x - s * eb.x, c * xa.y - s * eb.y);
+        Gs[b][col] = make_double2(s * xa.x + c * eb.x, s * xa.y + c * eb.y);
+      }
+      __syncthreads();
+    }
+    if (sh_sweep_off < 2e-15) break;
+    __syncthreads();
+  }
+  // sort eigenvalues descending: perm[rank] = index
+  if (t < PR) {
+    const double li = Gs[t][t].x;
+    int rank = 0;
+    for (int j = 0; j < PR; ++j) {
+      const double lj = Gs[j][j].x;
+      rank += (lj > li) || (lj == li && j < t);
+    }
+    perm[rank] = t;
+  }
+  __syncthreads();
+  // W^H planes with sorted columns: Aop[i][j] = conj(W[j][perm[i]])
+  for (int e = t; e < PR * PR; e += 256) {
+    const int i = e / PR, j = e % PR;
+    const cplx v = Ws[j][perm[i]];
+    Ps_re[i][j] = v.x;
+    Ps_im[i][j] = -v.y;
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: P <- W^H P over all LD columns (DMMA), in place ----------------
+  const int ntiles = ld / 8;
+  for (int nt8 = w; nt8 < ntiles; nt8 += 8) {
+    double br[4][2], bim[4][2], bn[4][2];
+    const int col = nt8 * 8 + gq;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const cplx x = Z[grow(ks * 8 + q + 4 * v) + col];
+        br[ks][v] = x.x; bim[ks][v] = x.y; bn[ks][v] = -x.y;
+      }
+    double cr[2][4], ci[2][4];
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) cr[m2][v] = ci[m2][v] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        double ar[4], ai[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int rr = m2 * 16 + gq + 8 * (v & 1), kk = ks * 8 + q + 4 * (v >> 1);
+          ar[v] = Ps_re[rr][kk]; ai[v] = Ps_im[rr][kk];
+        }
+        dmma16x8x8(cr[m2], ar, br[ks]);
+        dmma16x8x8(cr[m2], ai, bn[ks]);
+        dmma16x8x8(ci[m2], ar, bim[ks]);
+        dmma16x8x8(ci[m2], ai, br[ks]);
+      }
+    }
+#pragma unroll
+    for (int m2 = 0; m2 < 2; ++m2)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int rr = m2 * 16 + gq + 8 * (v >> 1);
+        Z[grow(rr) + nt8 * 8 + 2 * q + (v & 1)] = cmake(cr[m2][v], ci[m2][v]);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per chain: row norms -> singular values, rank sort, write U_k S_k and V_k^H, update slots
+__global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
+                                                           int n_slots, long long Z_, long long US_, long long Vh_, SvdGeom g,
+                                                           int keep, int nr_bulk, int slot_lognorm, int slot_trunc) {
+  extern __shared__ double dyn[];
+  double* s2 = dyn;                                   // p_pad
+  int* idx = reinterpret_cast<int*>(dyn + g.p_pad);   // keep
+  __shared__ double red[34];
+  cplx* cb = base + (long long)blockIdx.x * chain_stride;
+  const cplx* Z = cb + Z_;
+  cplx* US = cb + US_;
+  cplx* Vh = cb + Vh_;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  for (int i = w; i < g.p_pad; i += nw) {
+    double acc = 0.0;
+    const cplx* row = Z + (long long)i * g.ld;
+    for (int c = lane; c < g.q_pad; c += 32) acc += cabs2(row[c]);
+    acc = warp_sum(acc);
+    if (lane == 0) s2[i] = acc;
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int i = t; i < g.p_pad; i += blockDim.x) part += s2[i];
+  const double total = block_sum(part, red);
+  for (int i = t; i < g.p_pad; i += blockDim.x) {
+    const double si = s2[i];
+    int rank = 0;
+    for (int j = 0; j < g.p_pad; ++j) {
+      const double sj = s2[j];
+      rank += (sj > si) || (sj == si && j < i);
+    }
+    if (rank < keep) idx[rank] = i;
+  }
+  __syncthreads();
+  double disc = 0.0;
+  {
+    double kept = 0.0;
+    for (int k = t; k < keep; k += blockDim.x) kept += s2[idx[k]];
+    kept = block_sum(kept, red);
+    disc = total - kept;
+    if (disc < 0.0) disc = 0.0;
+  }
+  const double frob = sqrt(total);
+  const double scale = (nr_bulk && frob > 0.0) ? 1.0 / frob : 1.0;
+  const int m = g.m, n = g.n;
+  if (g.mode_t) {
+    // A = Yhat^T diag(s) conj(J):  US[r][k] = Y[idx_k][r] * scale ;  Vh[k][c] = conj(J[idx_k][c])
+    for (long long e = t; e < (long long)m * keep; e += blockDim.x) {
+      const int r = (int)(e / keep), k = (int)(e % keep);
+      US[e] = cscale(Z[(long long)idx[k] * g.ld + r], scale);
+    }
+    for (long long e = t; e < (long long)keep * n; e += blockDim.x) {
+      const int k = (int)(e / n), c = (int)(e % n);
+      Vh[e] = cconj(Z[(long long)idx[k] * g.ld + g.q_pad + c]);
+    }
+  } else {
+    // A = J^H diag(s) Yhat:  US[r][k] = conj(J[idx_k][r]) s_k scale ;  Vh[k][c] = Y[idx_k][c] / s_k
+    for (long long e = t; e < (long long)m * keep; e += blockDim.x) {
+      const int r = (int)(e / keep), k = (int)(e % keep);
+      US[e] = cscale(cconj(Z[(long long)idx[k] * g.ld + g.q_pad + r]), sqrt(s2[idx[k]]) * scale);
+    }
+    for (long long e = t; e < (long long)keep * n; e += blockDim.x) {
+      const int k = (int)(e / n), c = (int)(e % n);
+      const double sk = sqrt(s2[idx[k]]);
+      Vh[e] = sk > 0.0 ? cscale(Z[(long long)idx[k] * g.ld + c], 1.0 / sk) : cmake(0.0, 0.0);
+    }
+  }
+  if (t == 0) {
+    double* sl = slots + (long long)blockIdx.x * n_slots;
+    if (nr_bulk && slot_lognorm >= 0 && frob > 0.0) sl[slot_lognorm] += log(frob);
+    if (slot_trunc >= 0 && total > 0.0) sl[slot_trunc] += sqrt(disc / total);
+  }
+}
+
+__global__ void fill_kernel(double* p, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                 int nr_bulk, int slot_lognorm, int slot_trunc) {
+  if (m == 0 || n == 0) return 0;
+  SvdGeom g = svd_geom(m, n);
+  {
+    long long total = (long long)g.p_pad * g.ld;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    svd_init_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, A, work, g);
+    ++*a.launches;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(svd_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_ROUND_SMEM);
+    attr_set = true;
+  }
+  double* off0 = a.svd_off;
+  double* off1 = a.svd_off + a.nb;
+  fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(off1, a.nb, 1e300);   // "previous sweep" of sweep 0: not converged
+  ++*a.launches;
+  int sweeps = 0;
+  bool converged = false;
+  for (int s = 0; s < SVD_MAX_SWEEPS; ++s) {
+    double* cur = (s & 1) ? off1 : off0;
+    double* prev = (s & 1) ? off0 : off1;
+    cudaMemsetAsync(cur, 0, sizeof(double) * a.nb, a.stream);
+    for (int r = 0; r < g.nblk - 1; ++r) {
+      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur);
+      ++*a.launches;
+    }
+    cudaMemcpyAsync(a.svd_off_host, cur, sizeof(double) * a.nb, cudaMemcpyDeviceToHost, a.stream);
+    if (cudaStreamSynchronize(a.stream) != cudaSuccess) return -1;
+    ++sweeps;
+    double mx = 0.0;
+    for (int c = 0; c < a.nb; ++c) {
+      double v = a.svd_off_host[c];
+      if (!(v == v)) return -2;   // NaN
+      if (v > mx) mx = v;
+    }
+    if (mx < SVD_TOL) { converged = true; break; }
+  }
+  size_t dyn = sizeof(double) * g.p_pad + sizeof(int) * (size_t)keep + 16;
+  svd_extract_kernel<<<a.nb, 1024, dyn, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, work, US, Vh, g, (int)keep, nr_bulk,
+                                                     slot_lognorm, slot_trunc);
+  ++*a.launches;
+  return converged ? sweeps : -3;
+}
+
+}  // namespace kbp

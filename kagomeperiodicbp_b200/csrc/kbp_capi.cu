@@ -1,0 +1,334 @@
+// C ABI of libkbp.so (see include/kbp.h): context, device arena, transfers, tensor-program interpreter.
+#include "../../include/kbp.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kbp_ops.cuh"
+
+struct kbp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double2* arena = nullptr;
+  int64_t chain_elems = 0;
+  int nb = 0;
+  double* slots = nullptr;
+  int n_slots = 0;
+  double* svd_off = nullptr;
+  double* svd_off_host = nullptr;
+  int64_t launches = 0;
+  int64_t svd_sweeps = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+};
+
+static int fail(kbp_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define CU(c, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(c, KBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" {
+
+int kbp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int kbp_create(int device, kbp_ctx** out) {
+  if (!out) return KBP_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return KBP_E_CUDA;     // no CPU fallback: the caller must fail loudly
+  if (device < 0 || device >= n) return KBP_E_ARG;
+  kbp_ctx* c = new kbp_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    delete c;
+    return KBP_E_CUDA;
+  }
+  *out = c;
+  return KBP_OK;
+}
+
+static void free_arena(kbp_ctx* c) {
+  if (c->arena) cudaFree(c->arena);
+  if (c->slots) cudaFree(c->slots);
+  if (c->svd_off) cudaFree(c->svd_off);
+  if (c->svd_off_host) cudaFreeHost(c->svd_off_host);
+  c->arena = nullptr; c->slots = nullptr; c->svd_off = nullptr; c->svd_off_host = nullptr;
+  c->chain_elems = 0; c->nb = 0; c->n_slots = 0;
+}
+
+void kbp_destroy(kbp_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_arena(c);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* kbp_last_error(const kbp_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
+  if (!c || chain_elems <= 0 || nb <= 0 || n_slots <= 0) return fail(c, KBP_E_ARG, "kbp_reserve: bad argument");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (chain_elems > c->chain_elems || nb != c->nb || n_slots != c->n_slots) {
+    free_arena(c);
+    CU(c, cudaMalloc(&c->arena, sizeof(double2) * (size_t)chain_elems * nb));
+    CU(c, cudaMalloc(&c->slots, sizeof(double) * (size_t)nb * n_slots));
+    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * 2 * nb));
+    CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * nb));
+    c->chain_elems = chain_elems; c->nb = nb; c->n_slots = n_slots;
+  }
+  CU(c, cudaMemsetAsync(c->slots, 0, sizeof(double) * (size_t)nb * n_slots, c->stream));
+  return KBP_OK;
+}
+
+static int check_range(kbp_ctx* c, int chain, int64_t off, int64_t n) {
+  if (!c || !c->arena) return fail(c, KBP_E_ARG, "arena not reserved");
+  if (off < 0 || n < 0 || off + n > c->chain_elems || chain < -1 || chain >= c->nb) return fail(c, KBP_E_ARG, "transfer out of range");
+  return KBP_OK;
+}
+
+int kbp_upload(kbp_ctx* c, int chain, int64_t off, const void* host, int64_t n) {
+  int r = check_range(c, chain, off, n);
+  if (r) return r;
+  if (n == 0) return KBP_OK;
+  CU(c, cudaSetDevice(c->device));
+  if (chain >= 0) {
+    CU(c, cudaMemcpyAsync(c->arena + (size_t)chain * c->chain_elems + off, host, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CU(c, cudaMemcpy2DAsync(c->arena + off, sizeof(double2) * c->chain_elems, host, sizeof(double2) * n, sizeof(double2) * n, c->nb,
+                            cudaMemcpyHostToDevice, c->stream));
+  }
+  return KBP_OK;
+}
+
+int kbp_broadcast(kbp_ctx* c, int64_t off, const void* host, int64_t n) {
+  int r = check_range(c, 0, off, n);
+  if (r) return r;
+  if (n == 0) return KBP_OK;
+  CU(c, cudaSetDevice(c->device));
+  // pitch 0 on the source side repeats the same row for every chain
+  for (int b = 0; b < c->nb; ++b)
+    CU(c, cudaMemcpyAsync(c->arena + (size_t)b * c->chain_elems + off, host, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+  return KBP_OK;
+}
+
+int kbp_download(kbp_ctx* c, int chain, int64_t off, void* host, int64_t n) {
+  int r = check_range(c, chain, off, n);
+  if (r) return r;
+  if (n == 0) return KBP_OK;
+  CU(c, cudaSetDevice(c->device));
+  if (chain >= 0) {
+    CU(c, cudaMemcpyAsync(host, c->arena + (size_t)chain * c->chain_elems + off, sizeof(double2) * n, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    CU(c, cudaMemcpy2DAsync(host, sizeof(double2) * n, c->arena + off, sizeof(double2) * c->chain_elems, sizeof(double2) * n, c->nb,
+                            cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  return KBP_OK;
+}
+
+int kbp_slots_read(kbp_ctx* c, double* host) {
+  if (!c || !c->slots) return fail(c, KBP_E_ARG, "arena not reserved");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(host, c->slots, sizeof(double) * (size_t)c->nb * c->n_slots, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return KBP_OK;
+}
+
+int kbp_slots_zero(kbp_ctx* c) {
+  if (!c || !c->slots) return fail(c, KBP_E_ARG, "arena not reserved");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemsetAsync(c->slots, 0, sizeof(double) * (size_t)c->nb * c->n_slots, c->stream));
+  return KBP_OK;
+}
+
+int kbp_sync(kbp_ctx* c) {
+  if (!c) return KBP_E_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return KBP_OK;
+}
+
+int64_t kbp_svd_work_elems(int64_t m, int64_t n) { return kbp::svd_work_elems(m, n); }
+int64_t kbp_qr_work_elems(int64_t m, int64_t n) {
+  int64_t k = m < n ? m : n;
+  return m * n + m * k + k + 8;
+}
+int64_t kbp_launch_count(const kbp_ctx* c) { return c ? c->launches : 0; }
+int64_t kbp_svd_sweeps(const kbp_ctx* c) { return c ? c->svd_sweeps : 0; }
+
+int kbp_timer_start(kbp_ctx* c) {
+  if (!c) return KBP_E_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev0, c->stream));
+  return KBP_OK;
+}
+
+int kbp_timer_stop_ms(kbp_ctx* c, double* ms) {
+  if (!c || !ms) return KBP_E_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(c->ev1, c->stream));
+  CU(c, cudaEventSynchronize(c->ev1));
+  float f = 0.f;
+  CU(c, cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  *ms = f;
+  return KBP_OK;
+}
+
+static inline double bits_to_double(int64_t b) {
+  double d;
+  memcpy(&d, &b, sizeof(d));
+  return d;
+}
+
+int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
+  if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
+  CU(c, cudaSetDevice(c->device));
+  kbp::Arena a;
+  a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
+  a.stream = c->stream; a.launches = &c->launches; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  const int64_t E = c->chain_elems;
+  auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };
+  auto slot_ok = [&](int64_t s) { return s >= -1 && s < c->n_slots; };
+  int64_t i = 0;
+  int status = KBP_OK;
+  while (i < n_words) {
+    const int64_t op = w[i];
+    char where[64];
+    snprintf(where, sizeof(where), " (op %lld at word %lld)", (long long)op, (long long)i);
+#define NEED(k) if (i + 1 + (k) > n_words) return fail(c, KBP_E_PROGRAM, std::string("truncated program") + where)
+#define BAD(msg) return fail(c, KBP_E_PROGRAM, std::string(msg) + where)
+    switch (op) {
+      case KBP_OP_PERMUTE: {
+        NEED(4);
+        const int64_t dst = w[i + 1], src = w[i + 2], cj = w[i + 3], nd = w[i + 4];
+        if (nd < 1 || nd > 8) BAD("permute: ndim must be 1..8");
+        NEED(4 + 2 * nd);
+        const int64_t* dims = w + i + 5;
+        const int64_t* perm = dims + nd;
+        int64_t tot = 1;
+        bool seen[8] = {false};
+        for (int d = 0; d < nd; ++d) {
+          tot *= dims[d];
+          if (perm[d] < 0 || perm[d] >= nd || seen[perm[d]]) BAD("permute: bad permutation");
+          seen[perm[d]] = true;
+        }
+        if (!in_arena(dst, tot) || !in_arena(src, tot)) BAD("permute: buffer out of arena");
+        kbp::permute(a, dst, src, (int)cj, (int)nd, dims, perm);
+        i += 5 + 2 * nd;
+        break;
+      }
+      case KBP_OP_GEMM: {
+        NEED(8);
+        const int64_t C = w[i + 1], A = w[i + 2], B = w[i + 3], m = w[i + 4], n = w[i + 5], k = w[i + 6], oa = w[i + 7], ob = w[i + 8];
+        if (m < 0 || n < 0 || k < 0 || oa < 0 || oa > 3 || ob < 0 || ob > 3) BAD("gemm: bad argument");
+        if (!in_arena(C, m * n) || !in_arena(A, m * k) || !in_arena(B, k * n)) BAD("gemm: buffer out of arena");
+        kbp::gemm(a, C, A, B, m, n, k, (int)oa, (int)ob);
+        i += 9;
+        break;
+      }
+      case KBP_OP_QR: {
+        NEED(6);
+        const int64_t A = w[i + 1], Q = w[i + 2], R = w[i + 3], wk = w[i + 4], m = w[i + 5], n = w[i + 6];
+        if (m <= 0 || n <= 0) BAD("qr: bad shape");
+        const int64_t k = m < n ? m : n;
+        if (!in_arena(A, m * n) || !in_arena(Q, m * k) || !in_arena(R, k * n) || !in_arena(wk, kbp_qr_work_elems(m, n)))
+          BAD("qr: buffer out of arena");
+        kbp::qr(a, A, Q, R, wk, m, n);
+        i += 7;
+        break;
+      }
+      case KBP_OP_SVD: {
+        NEED(10);
+        const int64_t A = w[i + 1], US = w[i + 2], Vh = w[i + 3], wk = w[i + 4], m = w[i + 5], n = w[i + 6], keep = w[i + 7];
+        const int64_t nrb = w[i + 8], s0 = w[i + 9], s1 = w[i + 10];
+        if (m <= 0 || n <= 0 || keep <= 0 || keep > (m < n ? m : n) || !slot_ok(s0) || !slot_ok(s1)) BAD("svd: bad argument");
+        if (!in_arena(A, m * n) || !in_arena(US, m * keep) || !in_arena(Vh, keep * n) || !in_arena(wk, kbp::svd_work_elems(m, n)))
+          BAD("svd: buffer out of arena");
+        int sw = kbp::svd_truncate(a, A, US, Vh, wk, m, n, keep, (int)nrb, (int)s0, (int)s1);
+        if (sw == -1) return fail(c, KBP_E_CUDA, std::string("svd: ") + cudaGetErrorString(cudaGetLastError()) + where);
+        if (sw == -2) { status = KBP_E_NONFINITE; c->err = std::string("svd: non-finite input") + where; }
+        else if (sw == -3) { if (status == KBP_OK) { status = KBP_E_SVD_NOCONV; c->err = std::string("svd: Jacobi did not converge") + where; } }
+        else c->svd_sweeps += sw;
+        i += 11;
+        break;
+      }
+      case KBP_OP_NORMALIZE: {
+        NEED(3);
+        if (!in_arena(w[i + 1], w[i + 2]) || !slot_ok(w[i + 3])) BAD("normalize: bad argument");
+        kbp::normalize(a, w[i + 1], w[i + 2], (int)w[i + 3]);
+        i += 4;
+        break;
+      }
+      case KBP_OP_EMBED: {
+        NEED(11);
+        const int64_t dst = w[i + 1], src = w[i + 2], d0 = w[i + 5], d1 = w[i + 6], d2 = w[i + 7], s0 = w[i + 8], s1 = w[i + 9], s2 = w[i + 10];
+        if (d0 < 0 || d1 < 0 || d2 < 0 || !slot_ok(w[i + 11])) BAD("embed: bad argument");
+        if (d0 * d1 * d2 > 0) {
+          const int64_t last = (d0 - 1) * s0 + (d1 - 1) * s1 + (d2 - 1) * s2;
+          if (!in_arena(src, d0 * d1 * d2) || dst < 0 || s0 < 0 || s1 < 0 || s2 < 0 || dst + last >= E) BAD("embed: buffer out of arena");
+        }
+        kbp::embed(a, dst, src, bits_to_double(w[i + 3]), bits_to_double(w[i + 4]), d0, d1, d2, s0, s1, s2, (int)w[i + 11]);
+        i += 12;
+        break;
+      }
+      case KBP_OP_ZERO: {
+        NEED(2);
+        if (!in_arena(w[i + 1], w[i + 2])) BAD("zero: buffer out of arena");
+        kbp::zero(a, w[i + 1], w[i + 2]);
+        i += 3;
+        break;
+      }
+      case KBP_OP_SCALAR_TO_SLOT: {
+        NEED(3);
+        if (!in_arena(w[i + 1], 1) || !slot_ok(w[i + 2]) || !slot_ok(w[i + 3])) BAD("scalar_to_slot: bad argument");
+        kbp::scalar_to_slot(a, w[i + 1], (int)w[i + 2], (int)w[i + 3]);
+        i += 4;
+        break;
+      }
+      case KBP_OP_NONFINITE: {
+        NEED(3);
+        if (!in_arena(w[i + 1], w[i + 2]) || !slot_ok(w[i + 3]) || w[i + 3] < 0) BAD("nonfinite: bad argument");
+        kbp::count_nonfinite(a, w[i + 1], w[i + 2], (int)w[i + 3]);
+        i += 4;
+        break;
+      }
+      case KBP_OP_EYE: {
+        NEED(3);
+        if (w[i + 2] < 0 || w[i + 3] < 0 || !in_arena(w[i + 1], w[i + 2] * w[i + 3])) BAD("eye: buffer out of arena");
+        kbp::eye(a, w[i + 1], w[i + 2], w[i + 3]);
+        i += 4;
+        break;
+      }
+      default:
+        BAD("unknown opcode");
+    }
+#undef NEED
+#undef BAD
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, KBP_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return status;
+}
+
+}  // extern "C"

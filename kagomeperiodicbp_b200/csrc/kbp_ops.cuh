@@ -1,0 +1,50 @@
+// Host-side launchers of the batched complex128 kernels.  Every launcher works on `nb` independent
+// chains laid out in one arena: chain c's copy of a buffer lives at  base + c*chain_stride + offset
+// (complex128 elements).  All launches are asynchronous on `stream`; none synchronises except
+// svd_truncate (one flag read per Jacobi sweep).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kbp {
+
+struct Arena {
+  double2* base;          // nb * chain_stride complex128 elements
+  int64_t chain_stride;   // elements per chain
+  double* slots;          // nb * n_slots doubles (log-norms, truncation errors, flags)
+  int n_slots;
+  int nb;
+  cudaStream_t stream;
+  int64_t* launches;      // host counter of kernel launches
+  // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
+  double* svd_off;        // device: [2][nb]
+  double* svd_off_host;   // pinned host mirror: [nb]
+};
+
+enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };   // as-is, transpose, conj-transpose, conj
+
+// dst[contiguous, shape dims_src[perm]] = (conj?) src[contiguous, shape dims_src] transposed by perm
+void permute(const Arena& a, int64_t dst, int64_t src, int conj, int ndim, const int64_t* dims_src, const int64_t* perm);
+// C(m x n) = opA(A) * opB(B), row-major, inner dimension k
+void gemm(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB);
+// A(m x n) = Q(m x r) R(r x n), r = min(m, n), Q^H Q = I.  work: m*n + n elements
+void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);
+// rank-`keep` truncated SVD of A(m x n):  US(m x keep) = U_k diag(s_k) [ / ||A||_F if nr_bulk ],  Vh(keep x n).
+// slot_lognorm += ln ||A||_F (if nr_bulk); slot_trunc += sqrt(sum_discarded s^2 / sum s^2).
+// work: see svd_work_elems().  Returns the number of Jacobi sweeps used (max over chains), <0 on failure.
+int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                 int nr_bulk, int slot_lognorm, int slot_trunc);
+int64_t svd_work_elems(int64_t m, int64_t n);
+// buf /= ||buf||_F ; slot += ln ||buf||_F
+void normalize(const Arena& a, int64_t buf, int64_t n, int slot_lognorm);
+// dst[dst_off + i*s0 + j*s1 + k*s2] = alpha * src[(i*d1 + j)*d2 + k]; if sign_slot >= 0, alpha *= sign(slots[sign_slot]) (>0 -> +1, else -1)
+void embed(const Arena& a, int64_t dst, int64_t src, double alpha_re, double alpha_im, int64_t d0, int64_t d1, int64_t d2,
+           int64_t s0, int64_t s1, int64_t s2, int sign_slot);
+void zero(const Arena& a, int64_t dst, int64_t n);
+void eye(const Arena& a, int64_t dst, int64_t rows, int64_t cols);
+// slots[slot_re], slots[slot_im] = buf[0]   (copy a device scalar into the slot table)
+void scalar_to_slot(const Arena& a, int64_t buf, int slot_re, int slot_im);
+// NaN/Inf guard: slots[slot] += (number of non-finite entries in buf)
+void count_nonfinite(const Arena& a, int64_t buf, int64_t n, int slot);
+
+}  // namespace kbp

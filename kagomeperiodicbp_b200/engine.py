@@ -1,0 +1,167 @@
+"""ctypes binding of libkbp.so (the C ABI in include/kbp.h) -- the only way numerical work leaves
+Python in this package.  There is NO CPU fallback: if the library or a CUDA device is missing,
+``Engine()`` raises ``EngineUnavailable`` and every compute entry point of the package fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkbp.so")
+
+OP_PERMUTE, OP_GEMM, OP_QR, OP_SVD, OP_NORMALIZE, OP_EMBED, OP_ZERO, OP_SCALAR_TO_SLOT, OP_NONFINITE, OP_EYE = range(1, 11)
+E_SVD_NOCONV, E_NONFINITE = -4, -5
+
+EXPORTED = [
+    "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
+    "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
+    "kbp_qr_work_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_timer_start", "kbp_timer_stop_ms",
+]
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+class BubbleConError(RuntimeError):
+    """raised where the reference prints and calls exit(1) (src/libs/bubblecon.py:2921-2949,
+    src/libs/bmpslib.py:711-717); name follows src/_error_types.py."""
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise EngineUnavailable(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        P, I, L, D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+        lib.kbp_create.argtypes = [I, ctypes.POINTER(P)]; lib.kbp_create.restype = I
+        lib.kbp_destroy.argtypes = [P]; lib.kbp_destroy.restype = None
+        lib.kbp_last_error.argtypes = [P]; lib.kbp_last_error.restype = ctypes.c_char_p
+        lib.kbp_device_count.argtypes = []; lib.kbp_device_count.restype = I
+        lib.kbp_reserve.argtypes = [P, L, I, I]; lib.kbp_reserve.restype = I
+        lib.kbp_upload.argtypes = [P, I, L, P, L]; lib.kbp_upload.restype = I
+        lib.kbp_download.argtypes = [P, I, L, P, L]; lib.kbp_download.restype = I
+        lib.kbp_broadcast.argtypes = [P, L, P, L]; lib.kbp_broadcast.restype = I
+        lib.kbp_slots_read.argtypes = [P, P]; lib.kbp_slots_read.restype = I
+        lib.kbp_slots_zero.argtypes = [P]; lib.kbp_slots_zero.restype = I
+        lib.kbp_run.argtypes = [P, P, L]; lib.kbp_run.restype = I
+        lib.kbp_sync.argtypes = [P]; lib.kbp_sync.restype = I
+        lib.kbp_svd_work_elems.argtypes = [L, L]; lib.kbp_svd_work_elems.restype = L
+        lib.kbp_qr_work_elems.argtypes = [L, L]; lib.kbp_qr_work_elems.restype = L
+        lib.kbp_launch_count.argtypes = [P]; lib.kbp_launch_count.restype = L
+        lib.kbp_svd_sweeps.argtypes = [P]; lib.kbp_svd_sweeps.restype = L
+        lib.kbp_timer_start.argtypes = [P]; lib.kbp_timer_start.restype = I
+        lib.kbp_timer_stop_ms.argtypes = [P, ctypes.POINTER(D)]; lib.kbp_timer_stop_ms.restype = I
+        _lib = lib
+        return lib
+
+
+def svd_work_elems(m: int, n: int) -> int:
+    """pure-integer mirror of kbp_svd_work_elems so programs can be compiled without a device."""
+    p, q = (n, m) if m >= n else (m, n)
+    p_pad = (p + 31) // 32 * 32
+    q_pad = (q + 7) // 8 * 8
+    return p_pad * (q_pad + p_pad)
+
+
+def qr_work_elems(m: int, n: int) -> int:
+    k = min(m, n)
+    return m * n + m * k + k + 8
+
+
+class Engine:
+    """one CUDA context-stream + device arena holding ``nb`` chains."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        if self.lib.kbp_device_count() <= 0:
+            raise EngineUnavailable("no CUDA device visible: the block-BP engine has no CPU fallback")
+        h = ctypes.c_void_p()
+        rc = self.lib.kbp_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise EngineUnavailable(f"kbp_create(device={device}) failed with code {rc}")
+        self.h = h
+        self.device = device
+        self.nb = 0
+        self.n_slots = 0
+        self.chain_elems = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kbp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, soft=()):
+        if rc == 0 or rc in soft:
+            return rc
+        raise BubbleConError(f"libkbp error {rc}: {self.lib.kbp_last_error(self.h).decode()}")
+
+    def reserve(self, chain_elems: int, nb: int, n_slots: int = 16):
+        self._check(self.lib.kbp_reserve(self.h, int(chain_elems), int(nb), int(n_slots)))
+        self.nb, self.n_slots = nb, n_slots
+        self.chain_elems = int(chain_elems)
+
+    def upload(self, offset: int, arr: np.ndarray, chain: int = -1):
+        """``arr``: [nb, n] (chain=-1) or [n] complex128."""
+        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        n = a.shape[-1] if chain < 0 else a.size
+        if chain < 0:
+            assert a.ndim == 2 and a.shape[0] == self.nb
+        self._check(self.lib.kbp_upload(self.h, chain, int(offset), a.ctypes.data_as(ctypes.c_void_p), int(n)))
+
+    def broadcast(self, offset: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=np.complex128).ravel()
+        self._check(self.lib.kbp_broadcast(self.h, int(offset), a.ctypes.data_as(ctypes.c_void_p), int(a.size)))
+
+    def download(self, offset: int, n: int, chain: int = -1) -> np.ndarray:
+        out = np.empty((self.nb, n) if chain < 0 else (n,), dtype=np.complex128)
+        self._check(self.lib.kbp_download(self.h, chain, int(offset), out.ctypes.data_as(ctypes.c_void_p), int(n)))
+        return out
+
+    def slots(self) -> np.ndarray:
+        out = np.empty((self.nb, self.n_slots), dtype=np.float64)
+        self._check(self.lib.kbp_slots_read(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def slots_zero(self):
+        self._check(self.lib.kbp_slots_zero(self.h))
+
+    def run(self, words: np.ndarray, soft_errors=()):
+        w = np.ascontiguousarray(words, dtype=np.int64)
+        return self._check(self.lib.kbp_run(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)), soft=soft_errors)
+
+    def sync(self):
+        self._check(self.lib.kbp_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.kbp_launch_count(self.h))
+
+    def svd_sweeps(self) -> int:
+        return int(self.lib.kbp_svd_sweeps(self.h))
+
+    def timer_start(self):
+        self._check(self.lib.kbp_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = ctypes.c_double()
+        self._check(self.lib.kbp_timer_stop_ms(self.h, ctypes.byref(ms)))
+        return float(ms.value)

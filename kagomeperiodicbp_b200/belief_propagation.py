@@ -101,29 +101,25 @@ def _raw_initial_sites(D: int, L: int, random: bool, rng):
     return sites
 
 
-def _canonicalize_program(shapes):
-    key = ("canon", tuple(shapes))
-    if key not in _cache:
-        p = Program(N_SLOTS)
-        ins = [(f"s{k}", p.input(f"s{k}", sh)) for k, sh in enumerate(shapes)]
-        mp = DevMPS(p, len(shapes))
-        for k, (_, t) in enumerate(ins):
-            mp.set_site(t, k)
-        mp.left_canonical_QR()
-        last = p.copy(mp.A[-1])
-        p.normalize_(last, SLOT_LOGNORM)
-        mp.A[-1] = last
-        _cache[key] = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mp.A)])
-    return _cache[key]
-
-
 def initial_message(D: int, N: int, message_model: str = "RQ", rng=None) -> MPS:
-    """``N`` = number of MPS sites (= 2*block_size - 1), as in the reference's signature."""
-    raw = _raw_initial_sites(D, N, message_model in ("RQ", "RANDOM_QUANTUM"), rng)
-    comp = _canonicalize_program([s.shape for s in raw])
-    outs, _, _ = comp.run(get_engine("setup"), [{f"s{k}": s for k, s in enumerate(raw)}])
-    m = MPS.from_sites([outs[0][f"o{k}"] for k in range(N)], Corder=["L"] * (N - 1) + [None])
-    return m
+    """``N`` = number of MPS sites (= 2*block_size - 1), as in the reference's signature.
+
+    Setup data, not hot path: the message is a rank-1 product state embedded with bond D^2, so its
+    left-canonical form contains an ARBITRARY orthonormal completion of the null space of every bond, and
+    the first BP iteration depends on that choice (a partially swallowed message exposes the completion
+    columns to the truncation).  To start from the reference's exact tensors the completion must be LAPACK's,
+    i.e. numpy.linalg.qr on the host as in src/tensor_networks/mps.py:150-154 / src/libs/bmpslib.py:553-595.
+    For 'UQ' the result is a constant table that depends on (D, N) only."""
+    sites = _raw_initial_sites(D, N, message_model in ("RQ", "RANDOM_QUANTUM"), rng)
+    corder = [None] * N
+    for i in range(N - 1):
+        D1, d, D2 = sites[i].shape
+        Q, R = np.linalg.qr(sites[i].reshape(D1 * d, D2))
+        sites[i] = Q.reshape(D1, d, Q.shape[1])
+        corder[i] = "L"
+        sites[i + 1] = np.tensordot(R, sites[i + 1], axes=([1], [0]))
+    sites[N - 1] = sites[N - 1] / np.linalg.norm(sites[N - 1])
+    return MPS.from_sites(sites, Corder=corder)
 
 
 def initial_messages(D: int, block_N: int, model: str = "UQ", rng=None) -> dict:

@@ -20,6 +20,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace kbp {
 
@@ -88,7 +89,7 @@ __device__ __forceinline__ unsigned long long dbl_bits_nonneg(double x) { return
 
 __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base, long long chain_stride, long long Z_, SvdGeom g,
                                                         int round, double tol, const double* __restrict__ off_prev,
-                                                        double* __restrict__ off_cur) {
+                                                        double* __restrict__ off_cur, const double* __restrict__ fro2, int dbg) {
   // shared: staged operand planes (phase 1) reused as W^H planes (phase 3); G and W for the eigensolve
   extern __shared__ __align__(16) unsigned char svd_smem[];
   cplx (*Gs)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem);
@@ -103,6 +104,8 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
 
   const int chain = blockIdx.y;
   if (off_prev[chain] < tol) return;            // this chain converged in the previous sweep
+  // rows whose norm is below 1e-17 ||A||_F are rounding residue of exactly dependent rows: treated as zero
+  const double floor2 = 1e-34 * fro2[chain];
   cplx* Z = base + (long long)chain * chain_stride + Z_;
   int bi, bj;
   rr_pair(g.nblk, round, blockIdx.x, bi, bj);
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
   for (int e = t; e < PR * PR; e += 256) {
     const int i = e / PR, j = e % PR;
     if (i < j) {
-      const double dd = Gs[i][i].x * Gs[j][j].x;
-      if (dd > 0.0) off = fmax(off, sqrt(cabs2(Gs[i][j]) / dd));
+      const double gi_ = Gs[i][i].x, gj_ = Gs[j][j].x;
+      if (gi_ > floor2 && gj_ > floor2) off = fmax(off, sqrt(cabs2(Gs[i][j]) / (gi_ * gj_)));
     }
   }
   off = warp_max(off);
@@ -191,8 +194,9 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
         cplx e = cmake(1.0, 0.0);
         const double dd = gaa * gbb;
         double ratio = 0.0;
-        if (ab > 0.0 && dd > 0.0) ratio = ab / sqrt(dd);
-        if (ab > 0.0 && (ratio > 1e-17 || !(dd > 0.0))) {
+        const bool live = gaa > floor2 && gbb > floor2;
+        if (ab > 0.0 && live) ratio = ab / sqrt(dd);
+        if (live && ratio > 1e-17) {
           const double zeta = (gbb - gaa) / (2.0 * ab);
           const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           c = 1.0 / sqrt(1.0 + tt * tt);
@@ -324,6 +328,7 @@ __global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ ba
   double part = 0.0;
   for (int i = t; i < g.p_pad; i += blockDim.x) part += s2[i];
   const double total = block_sum(part, red);
+  double disc_part = 0.0;
   for (int i = t; i < g.p_pad; i += blockDim.x) {
     const double si = s2[i];
     int rank = 0;
@@ -332,16 +337,10 @@ __global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ ba
       rank += (sj > si) || (sj == si && j < i);
     }
     if (rank < keep) idx[rank] = i;
+    else disc_part += si;                    // summed directly: total - kept would cancel
   }
   __syncthreads();
-  double disc = 0.0;
-  {
-    double kept = 0.0;
-    for (int k = t; k < keep; k += blockDim.x) kept += s2[idx[k]];
-    kept = block_sum(kept, red);
-    disc = total - kept;
-    if (disc < 0.0) disc = 0.0;
-  }
+  const double disc = block_sum(disc_part, red);
   const double frob = sqrt(total);
   const double scale = (nr_bulk && frob > 0.0) ? 1.0 / frob : 1.0;
   const int m = g.m, n = g.n;
@@ -374,6 +373,15 @@ __global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ ba
   }
 }
 
+__global__ void svd_fro_kernel(const cplx* __restrict__ base, long long chain_stride, long long A_, long long n, double* __restrict__ fro2) {
+  __shared__ double red[34];
+  const cplx* A = base + (long long)blockIdx.x * chain_stride + A_;
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += cabs2(A[i]);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) fro2[blockIdx.x] = acc;
+}
+
 __global__ void fill_kernel(double* p, int n, double v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -397,21 +405,30 @@ int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work
   }
   double* off0 = a.svd_off;
   double* off1 = a.svd_off + a.nb;
+  double* fro2 = a.svd_off + 2 * a.nb;
+  svd_fro_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, m * n, fro2);
+  ++*a.launches;
   fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(off1, a.nb, 1e300);   // "previous sweep" of sweep 0: not converged
   ++*a.launches;
   int sweeps = 0;
   bool converged = false;
+  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
   for (int s = 0; s < SVD_MAX_SWEEPS; ++s) {
     double* cur = (s & 1) ? off1 : off0;
     double* prev = (s & 1) ? off0 : off1;
     cudaMemsetAsync(cur, 0, sizeof(double) * a.nb, a.stream);
     for (int r = 0; r < g.nblk - 1; ++r) {
-      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur);
+      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur, fro2, 0);
       ++*a.launches;
     }
     cudaMemcpyAsync(a.svd_off_host, cur, sizeof(double) * a.nb, cudaMemcpyDeviceToHost, a.stream);
     if (cudaStreamSynchronize(a.stream) != cudaSuccess) return -1;
     ++sweeps;
+    if (debug) {
+      fprintf(stderr, "[kbp svd %lldx%lld] sweep %d off:", (long long)m, (long long)n, s);
+      for (int c = 0; c < a.nb; ++c) fprintf(stderr, " %.3e", a.svd_off_host[c]);
+      fprintf(stderr, "\n");
+    }
     double mx = 0.0;
     for (int c = 0; c < a.nb; ++c) {
       double v = a.svd_off_host[c];

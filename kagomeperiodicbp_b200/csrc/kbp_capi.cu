@@ -93,7 +93,7 @@ int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
     free_arena(c);
     CU(c, cudaMalloc(&c->arena, sizeof(double2) * (size_t)chain_elems * nb));
     CU(c, cudaMalloc(&c->slots, sizeof(double) * (size_t)nb * n_slots));
-    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * 2 * nb));
+    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * 3 * nb));
     CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * nb));
     c->chain_elems = chain_elems; c->nb = nb; c->n_slots = n_slots;
   }

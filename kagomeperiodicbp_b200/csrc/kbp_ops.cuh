@@ -17,7 +17,7 @@ struct Arena {
   cudaStream_t stream;
   int64_t* launches;      // host counter of kernel launches
   // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
-  double* svd_off;        // device: [2][nb]
+  double* svd_off;        // device: [3][nb]  (off current / previous sweep, ||A||_F^2)
   double* svd_off_host;   // pinned host mirror: [nb]
 };
 

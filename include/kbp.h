@@ -84,6 +84,10 @@ int64_t kbp_launch_count(const kbp_ctx* ctx);
 int64_t kbp_svd_sweeps(const kbp_ctx* ctx);           /* total Jacobi sweeps so far */
 int kbp_timer_start(kbp_ctx* ctx);
 int kbp_timer_stop_ms(kbp_ctx* ctx, double* ms);       /* synchronises */
+/* per-opcode device time: when enabled, kbp_run brackets every op with CUDA events on the context's stream;
+ * kbp_profile_read synchronises and returns accumulated milliseconds and op counts indexed by opcode (16 entries) */
+int kbp_profile_enable(kbp_ctx* ctx, int on);
+int kbp_profile_read(kbp_ctx* ctx, double* ms16, int64_t* count16);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ constexpr int JB = 16;        // rows per block
 constexpr int PR = 2 * JB;    // rows per pair
 constexpr int KC = 32;        // columns staged per Gram step
 constexpr int LDP = KC + 4;   // shared row stride (doubles): 36 mod 16 == 4 -> conflict-free fragments
-constexpr size_t SVD_ROUND_SMEM = 2 * sizeof(double2) * PR * (PR + 1) + 2 * sizeof(double) * PR * LDP;
+constexpr size_t SVD_ROUND_SMEM = 3 * sizeof(double2) * PR * (PR + 1) + 2 * sizeof(double) * PR * LDP;
 constexpr double SVD_TOL = 1e-14;
 constexpr int SVD_MAX_SWEEPS = 40;
 
@@ -85,22 +85,44 @@ __device__ __forceinline__ void rr_pair(int n, int r, int t, int& a, int& b) {
   if (a > b) { int x = a; a = b; b = x; }
 }
 
+// Hermitian 2x2 Jacobi rotation for the pair (a, b): R = [[c, s], [-s e, c e]], e = exp(-i arg g_ab).
+// The dependent FP64 chain is the cost of a Jacobi step, so it is kept to two rsqrt: 1/|g_ab| (needed to
+// double precision: |e| must be 1) and 1/sqrt(1+t^2) (c^2+s^2 must be 1); tan(theta) itself only steers
+// the rotation and is evaluated in single precision -- the pair's off-diagonal drops by ~1e-7 per visit
+// instead of to zero, which the cyclic iteration absorbs.  Returns false (identity) for dead / tiny pairs.
+__device__ __forceinline__ bool jacobi_rot(double gaa, double gbb, cplx gab, double floor2, double& c, double& s, cplx& e) {
+  c = 1.0; s = 0.0; e = cmake(1.0, 0.0);
+  const double r2 = cabs2(gab);
+  if (!(gaa > floor2 && gbb > floor2) || !(r2 > 1e-34 * gaa * gbb)) return false;
+  const double inv_ab = rsqrt(r2);
+  const double ab2 = 2.0 * r2 * inv_ab, delta = gbb - gaa;
+  // tan(theta) = 2|g_ab| sgn(delta) / (|delta| + sqrt(delta^2 + 4|g_ab|^2)), operands brought into float range by
+  // a common power of two (live pairs have |g_ab|/|delta| >= 1e-34, so nothing underflows)
+  const int ex = ilogb(fmax(fabs(delta), ab2));
+  const float df = (float)scalbn(delta, -ex), af = (float)scalbn(ab2, -ex);
+  float tf = af / (fabsf(df) + sqrtf(fmaf(df, df, af * af)));
+  tf = copysignf(tf, df);
+  const double tt = (double)tf;
+  c = rsqrt(fma(tt, tt, 1.0));
+  s = tt * c;
+  e = cmake(gab.x * inv_ab, -gab.y * inv_ab);
+  return true;
+}
+
 __device__ __forceinline__ unsigned long long dbl_bits_nonneg(double x) { return (unsigned long long)__double_as_longlong(x); }
 
 __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base, long long chain_stride, long long Z_, SvdGeom g,
                                                         int round, double tol, const double* __restrict__ off_prev,
-                                                        double* __restrict__ off_cur, const double* __restrict__ fro2, int dbg) {
+                                                        double* __restrict__ off_cur, const double* __restrict__ fro2, int inner_max) {
   // shared: staged operand planes (phase 1) reused as W^H planes (phase 3); G and W for the eigensolve
   extern __shared__ __align__(16) unsigned char svd_smem[];
   cplx (*Gs)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem);
   cplx (*Ws)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem + sizeof(cplx) * PR * (PR + 1));
-  double (*Ps_re)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 2 * sizeof(cplx) * PR * (PR + 1));
-  double (*Ps_im)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 2 * sizeof(cplx) * PR * (PR + 1) + sizeof(double) * PR * LDP);
-  __shared__ double rot_c[JB], rot_s[JB];
-  __shared__ cplx rot_e[JB];
+  cplx (*G2)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem + 2 * sizeof(cplx) * PR * (PR + 1));
+  double (*Ps_re)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 3 * sizeof(cplx) * PR * (PR + 1));
+  double (*Ps_im)[LDP] = reinterpret_cast<double (*)[LDP]>(svd_smem + 3 * sizeof(cplx) * PR * (PR + 1) + sizeof(double) * PR * LDP);
   __shared__ double sh_red[34];
   __shared__ int perm[PR];
-  __shared__ double sh_sweep_off;
 
   const int chain = blockIdx.y;
   if (off_prev[chain] < tol) return;            // this chain converged in the previous sweep
@@ -179,67 +201,69 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
   if (off < tol) return;
 
   // ---------------- phase 2: Hermitian Jacobi eigensolve of G (shared memory) ----------------
+  // Parallel-ordered cyclic Jacobi: 31 steps of 16 disjoint rotations per sweep.  Thread (pr, qc) owns the
+  // 2x2 block rows{a_pr,b_pr} x cols{a_qc,b_qc}: it recomputes the two rotations it needs from the old G,
+  // applies R_pr^H . block . R_qc from buffer `cur` into buffer `cur^1`, and rotates its 2x2 block of W in
+  // place -- ONE barrier per step.  The solve stops once the largest |g_ab|/sqrt(g_aa g_bb) seen in a sweep is
+  // below max(2e-15, 1e-3 off^2): the residual it leaves is what the next outer sweep starts from, and
+  // the outer iteration converges quadratically, so early outer sweeps need no 1e-15 inner solve.
   for (int e = t; e < PR * PR; e += 256) Ws[e / PR][e % PR] = (e / PR == e % PR) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+  const double inner_tol = fmax(2e-15, 1e-3 * off * off);
+  int cur = 0;
+  const int pr = t >> 4, qc = t & 15;
   __syncthreads();
-  for (int isweep = 0; isweep < 15; ++isweep) {
-    if (t == 0) sh_sweep_off = 0.0;
+  for (int isweep = 0; isweep < inner_max; ++isweep) {
+    double my_off2 = 0.0;
     for (int step = 0; step < PR - 1; ++step) {
-      if (t < JB) {
-        int a, b;
-        rr_pair(PR, step, t, a, b);
-        const double gaa = Gs[a][a].x, gbb = Gs[b][b].x;
-        const cplx gab = Gs[a][b];
-        const double ab = sqrt(cabs2(gab));
-        double c = 1.0, s = 0.0;
-        cplx e = cmake(1.0, 0.0);
-        const double dd = gaa * gbb;
-        double ratio = 0.0;
-        const bool live = gaa > floor2 && gbb > floor2;
-        if (ab > 0.0 && live) ratio = ab / sqrt(dd);
-        if (live && ratio > 1e-17) {
-          const double zeta = (gbb - gaa) / (2.0 * ab);
-          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tt * tt);
-          s = tt * c;
-          e = cmake(gab.x / ab, -gab.y / ab);   // e^{-i phi}
-        }
-        rot_c[t] = c; rot_s[t] = s; rot_e[t] = e;
-        double mx = ratio;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0x0000ffffu, mx, o));
-        if (t == 0) sh_sweep_off = fmax(sh_sweep_off, mx);
+      cplx (*Go)[PR + 1] = cur ? G2 : Gs;
+      cplx (*Gn)[PR + 1] = cur ? Gs : G2;
+      int ap, bp, aq, bq;
+      rr_pair(PR, step, pr, ap, bp);
+      rr_pair(PR, step, qc, aq, bq);
+      double cp, sp, cq, sq;
+      cplx ep, eq;
+      jacobi_rot(Go[ap][ap].x, Go[bp][bp].x, Go[ap][bp], floor2, cp, sp, ep);
+      {
+        const double gaa = Go[aq][aq].x, gbb = Go[bq][bq].x;
+        const cplx gab = Go[aq][bq];
+        if (jacobi_rot(gaa, gbb, gab, floor2, cq, sq, eq) && pr == qc) my_off2 = fmax(my_off2, cabs2(gab) / (gaa * gbb));
       }
-      __syncthreads();
-      // column update  M <- M R  for G and W:  512 + 512 (row, pair) tasks
-      for (int task = t; task < 2 * PR * JB; task += 256) {
-        const int which = task / (PR * JB), rem = task % (PR * JB);
-        const int row = rem / JB, k = rem % JB;
-        int a, b;
-        rr_pair(PR, step, k, a, b);
-        const double c = rot_c[k], s = rot_s[k];
-        const cplx e = rot_e[k];
-        cplx (*M)[PR + 1] = which ? Ws : Gs;
-        const cplx xa = M[row][a], xb = M[row][b];
-        const cplx eb = cmul(e, xb);
-        M[row][a] = make_double2(c * xa.x - s * eb.x, c * xa.y - s * eb.y);
-        M[row][b] = make_double2(s * xa.x + c * eb.x, s * xa.y + c * eb.y);
-      }
-      __syncthreads();
-      // row update  G <- R^H G
-      for (int task = t; task < PR * JB; task += 256) {
-        const int col = task / JB, k = task % JB;
-        int a, b;
-        rr_pair(PR, step, k, a, b);
-        const double c = rot_c[k], s = rot_s[k];
-        const cplx ec = cconj(rot_e[k]);         // e^{+i phi}
-        const cplx xa = Gs[a][col], xb = Gs[b][col];
-        const cplx eb = cmul(ec, xb);
-        Gs[a][col] = make_double2(c * xa.x - s * eb.x, c * xa.y - s * eb.y);
-        Gs[b][col] = make_double2(s * xa.x + c * eb.x, s * xa.y + c * eb.y);
-      }
+      // column rotation R_q = [[c, s], [-s e, c e]] on columns (aq, bq), then row rotation R_p^H on rows (ap, bp)
+      const cplx x00 = Go[ap][aq], x01 = Go[ap][bq], x10 = Go[bp][aq], x11 = Go[bp][bq];
+      const cplx e01 = cmul(eq, x01), e11 = cmul(eq, x11);
+      const cplx y00 = make_double2(cq * x00.x - sq * e01.x, cq * x00.y - sq * e01.y);
+      const cplx y01 = make_double2(sq * x00.x + cq * e01.x, sq * x00.y + cq * e01.y);
+      const cplx y10 = make_double2(cq * x10.x - sq * e11.x, cq * x10.y - sq * e11.y);
+      const cplx y11 = make_double2(sq * x10.x + cq * e11.x, sq * x10.y + cq * e11.y);
+      const cplx epc = cconj(ep);
+      const cplx f10 = cmul(epc, y10), f11 = cmul(epc, y11);
+      cplx z00 = make_double2(cp * y00.x - sp * f10.x, cp * y00.y - sp * f10.y);
+      cplx z01 = make_double2(cp * y01.x - sp * f11.x, cp * y01.y - sp * f11.y);
+      cplx z10 = make_double2(sp * y00.x + cp * f10.x, sp * y00.y + cp * f10.y);
+      cplx z11 = make_double2(sp * y01.x + cp * f11.x, sp * y01.y + cp * f11.y);
+      if (pr == qc) { z00.y = 0.0; z11.y = 0.0; }   // diagonal of a Hermitian matrix
+      Gn[ap][aq] = z00; Gn[ap][bq] = z01; Gn[bp][aq] = z10; Gn[bp][bq] = z11;
+      // W <- W R_q on this thread's 2x2 block (rows ap, bp)
+      const cplx w00 = Ws[ap][aq], w01 = Ws[ap][bq], w10 = Ws[bp][aq], w11 = Ws[bp][bq];
+      const cplx g01 = cmul(eq, w01), g11 = cmul(eq, w11);
+      Ws[ap][aq] = make_double2(cq * w00.x - sq * g01.x, cq * w00.y - sq * g01.y);
+      Ws[ap][bq] = make_double2(sq * w00.x + cq * g01.x, sq * w00.y + cq * g01.y);
+      Ws[bp][aq] = make_double2(cq * w10.x - sq * g11.x, cq * w10.y - sq * g11.y);
+      Ws[bp][bq] = make_double2(sq * w10.x + cq * g11.x, sq * w10.y + cq * g11.y);
+      cur ^= 1;
       __syncthreads();
     }
-    if (sh_sweep_off < 2e-15) break;
+    my_off2 = warp_max(my_off2);
+    if (lane == 0) sh_red[w] = my_off2;
+    __syncthreads();
+    double so = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) so = fmax(so, sh_red[k]);
+    __syncthreads();
+    if (so < inner_tol * inner_tol) break;
+  }
+  if (cur) {                                      // final G lives in G2: the sort below reads Gs diagonals
+    if (t < PR) Gs[t][t] = G2[t][t];
     __syncthreads();
   }
   // sort eigenvalues descending: perm[rank] = index
@@ -413,12 +437,13 @@ int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work
   int sweeps = 0;
   bool converged = false;
   static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
+  static const int inner_max = getenv("KBP_SVD_INNER") ? atoi(getenv("KBP_SVD_INNER")) : 2;
   for (int s = 0; s < SVD_MAX_SWEEPS; ++s) {
     double* cur = (s & 1) ? off1 : off0;
     double* prev = (s & 1) ? off0 : off1;
     cudaMemsetAsync(cur, 0, sizeof(double) * a.nb, a.stream);
     for (int r = 0; r < g.nblk - 1; ++r) {
-      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur, fro2, 0);
+      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur, fro2, s < 24 ? inner_max : 15);
       ++*a.launches;
     }
     cudaMemcpyAsync(a.svd_off_host, cur, sizeof(double) * a.nb, cudaMemcpyDeviceToHost, a.stream);

@@ -22,6 +22,11 @@ struct kbp_ctx {
   double* svd_off_host = nullptr;
   int64_t launches = 0;
   int64_t svd_sweeps = 0;
+  bool profile = false;
+  struct Span { int op; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  double prof_ms[16] = {0};
+  int64_t prof_n[16] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
 };
@@ -195,6 +200,27 @@ int kbp_timer_stop_ms(kbp_ctx* c, double* ms) {
   return KBP_OK;
 }
 
+int kbp_profile_enable(kbp_ctx* c, int on) {
+  if (!c) return KBP_E_ARG;
+  c->profile = on != 0;
+  return KBP_OK;
+}
+
+int kbp_profile_read(kbp_ctx* c, double* ms16, int64_t* count16) {
+  if (!c || !ms16 || !count16) return KBP_E_ARG;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (auto& sp : c->spans) {
+    float f = 0.f;
+    if (cudaEventElapsedTime(&f, sp.a, sp.b) == cudaSuccess && sp.op >= 0 && sp.op < 16) { c->prof_ms[sp.op] += f; c->prof_n[sp.op] += 1; }
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  c->spans.clear();
+  for (int i = 0; i < 16; ++i) { ms16[i] = c->prof_ms[i]; count16[i] = c->prof_n[i]; c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  return KBP_OK;
+}
+
 static inline double bits_to_double(int64_t b) {
   double d;
   memcpy(&d, &b, sizeof(d));
@@ -218,6 +244,8 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
     snprintf(where, sizeof(where), " (op %lld at word %lld)", (long long)op, (long long)i);
 #define NEED(k) if (i + 1 + (k) > n_words) return fail(c, KBP_E_PROGRAM, std::string("truncated program") + where)
 #define BAD(msg) return fail(c, KBP_E_PROGRAM, std::string(msg) + where)
+    cudaEvent_t pa = nullptr, pb = nullptr;
+    if (c->profile) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, c->stream); }
     switch (op) {
       case KBP_OP_PERMUTE: {
         NEED(4);
@@ -323,9 +351,10 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
       default:
         BAD("unknown opcode");
     }
+    if (c->profile) { cudaEventRecord(pb, c->stream); c->spans.push_back({(int)op, pa, pb}); }
+  }
 #undef NEED
 #undef BAD
-  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, KBP_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
   return status;

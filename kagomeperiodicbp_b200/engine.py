@@ -20,6 +20,7 @@ EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
     "kbp_qr_work_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_timer_start", "kbp_timer_stop_ms",
+    "kbp_profile_enable", "kbp_profile_read",
 ]
 
 
@@ -65,6 +66,8 @@ def load_library():
         lib.kbp_svd_sweeps.argtypes = [P]; lib.kbp_svd_sweeps.restype = L
         lib.kbp_timer_start.argtypes = [P]; lib.kbp_timer_start.restype = I
         lib.kbp_timer_stop_ms.argtypes = [P, ctypes.POINTER(D)]; lib.kbp_timer_stop_ms.restype = I
+        lib.kbp_profile_enable.argtypes = [P, I]; lib.kbp_profile_enable.restype = I
+        lib.kbp_profile_read.argtypes = [P, P, P]; lib.kbp_profile_read.restype = I
         _lib = lib
         return lib
 
@@ -157,6 +160,15 @@ class Engine:
 
     def svd_sweeps(self) -> int:
         return int(self.lib.kbp_svd_sweeps(self.h))
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.kbp_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        ms = np.zeros(16)
+        cnt = np.zeros(16, dtype=np.int64)
+        self._check(self.lib.kbp_profile_read(self.h, ms.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p)))
+        return ms, cnt
 
     def timer_start(self):
         self._check(self.lib.kbp_timer_start(self.h))

@@ -34,7 +34,8 @@ SLOT_IP_RE, SLOT_IP_IM = 3, 4
 SLOT_TRUNC_DAMP = 5
 N_SLOTS = 8
 
-_pool = ThreadPoolExecutor(max_workers=6, thread_name_prefix="kbp-side")
+import os as _os
+_pool = ThreadPoolExecutor(max_workers=int(_os.environ.get("KBP_SIDE_THREADS", "6")), thread_name_prefix="kbp-side")
 _cache: dict = {}
 
 
@@ -189,7 +190,7 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
         opp = SIDE_OPPOSITE[side]
         # _fix_messages: right-canonical + unit norm (reference :113-117)
         mp.right_canonical(nr_bulk=True)
-        for k, t in enumerate(mp.A):
+        for k, t in enumerate(mp.dense_sites()):
             outs.append((f"out{k}", t))
             p.nonfinite(t, SLOT_NONFINITE)
         prev = DevMPS(p, L)
@@ -202,10 +203,10 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
             comb.slot_lognorm, comb.slot_trunc = SLOT_LOGNORM, SLOT_TRUNC_DAMP
             comb.left_canonical_QR()
             comb.right_canonical(maxD=chi, nr_bulk=True)
-            for k, t in enumerate(comb.A):
+            for k, t in enumerate(comb.dense_sites()):
                 outs.append((f"next{k}", t))
     else:
-        for k, t in enumerate(mp.A):
+        for k, t in enumerate(mp.dense_sites()):
             outs.append((f"out{k}", t))
     comp = Compiled(p, ins, outs, meta=dict(n_out=mp.N, L=L, side=side, svd_shapes=list(p.svd_shapes),
                                             qr_shapes=list(p.qr_shapes), gemm_flops=p.gemm_flops))
@@ -303,7 +304,7 @@ def _hermitize_program(shapes) -> Compiled:
         Dmax = max(Dmax, DL)
     mpC = add_two_mps(p, mpA, 0.5, mpB, 0.5)
     mpC.reduceD(Dmax)
-    comp = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mpC.A)])
+    comp = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mpC.dense_sites())])
     _cache[key] = comp
     return comp
 

@@ -54,9 +54,10 @@ def compile_bubblecon(T_list, edges_list, angles_list, bubble_angle, swallow_ord
             ins.append((f"t{a}", dts[a]))
     TL = [dts.get(alias[i]) for i in range(n)]
     mp, edges = trace_bubblecon(p, TL, edges_list, angles_list, bubble_angle, list(swallow_order), D_trunc, ket_tensors)
-    for t in mp.A:
+    sites = mp.dense_sites()
+    for t in sites:
         p.nonfinite(t, SLOT_NONFINITE)
-    comp = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(mp.A)], meta=dict(edges=edges, n_out=mp.N))
+    comp = Compiled(p, ins, [(f"o{k}", t) for k, t in enumerate(sites)], meta=dict(edges=edges, n_out=mp.N))
     _cache[key] = comp
     return comp, alias
 

@@ -31,23 +31,39 @@ __global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ 
 
   for (int j = 0; j < kk; ++j) {
     cplx* x = W + (long long)j * m;
-    double sig = 0.0;
-    for (int i = j + 1 + t; i < m; i += nt) sig += cabs2(x[i]);
+    // column scale first: boundary-MPS columns can sit at 1e-150 (rows that the truncation emptied), where
+    // squaring underflows -- all norms are formed from entries divided by the column's largest component
+    double cmx = 0.0;
+    for (int i = j + t; i < m; i += nt) cmx = fmax(cmx, fmax(fabs(x[i].x), fabs(x[i].y)));
+    cmx = warp_max(cmx);
+    __syncthreads();
+    if (lane == 0) red[w] = cmx;
+    __syncthreads();
+    if (w == 0) {
+      double v = lane < nw ? red[lane] : 0.0;
+      v = warp_max(v);
+      if (lane == 0) red[33] = v;
+    }
+    __syncthreads();
+    cmx = red[33];
+    const double cinv = cmx > 0.0 ? 1.0 / cmx : 0.0;
+    double sig = 0.0;                                   // scaled:  sum_{i>j} |x_i / cmx|^2
+    for (int i = j + 1 + t; i < m; i += nt) { const cplx y = cscale(x[i], cinv); sig += cabs2(y); }
     sig = block_sum(sig, red);
     if (t == 0) {
-      cplx alpha = x[j];
-      double absa = sqrt(cabs2(alpha));
-      double nrm = sqrt(fma(absa, absa, sig));
-      if (nrm == 0.0) {
+      const cplx alpha = x[j];
+      const cplx as = cscale(alpha, cinv);
+      const double absa_s = sqrt(cabs2(as));
+      const double nrm_s = sqrt(fma(absa_s, absa_s, sig));
+      if (!(cmx > 0.0) || nrm_s == 0.0) {
         sh_tau = 0.0; sh_s = cmake(0.0, 0.0); sh_inv_u0 = cmake(0.0, 0.0);
       } else {
-        cplx ph = absa > 0.0 ? cscale(alpha, 1.0 / absa) : cmake(1.0, 0.0);
-        cplx s = cscale(ph, -nrm);
-        cplx u0 = csub(alpha, s);                       // = ph * (absa + nrm): no cancellation
-        double u02 = cabs2(u0);
-        sh_tau = 2.0 * u02 / (u02 + sig);
-        sh_inv_u0 = cscale(cconj(u0), 1.0 / u02);
-        sh_s = s;
+        const cplx ph = absa_s > 0.0 ? cscale(as, 1.0 / absa_s) : cmake(1.0, 0.0);
+        const double u0_s = absa_s + nrm_s;               // |u0| / cmx : no cancellation, no squaring of tiny numbers
+        const double r = sqrt(sig) / u0_s;                // <= 1
+        sh_tau = 2.0 / (1.0 + r * r);                     // = 2 |u0|^2 / (|u0|^2 + sum_{i>j} |x_i|^2)
+        sh_inv_u0 = cscale(cconj(ph), cinv / u0_s);       // 1 / u0,  u0 = ph (|alpha| + ||x||)
+        sh_s = cscale(ph, -nrm_s * cmx);                  // R_jj
       }
       tau[j] = sh_tau;
     }

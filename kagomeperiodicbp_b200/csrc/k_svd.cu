@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
     if (t < PR) Gs[t][t] = G2[t][t];
     __syncthreads();
   }
-  // sort eigenvalues descending: perm[rank] = index
+  // sort eigenvalues descending: perm[rank] = index  (identity first, so that non-finite input can never index out of bounds)
+  if (t < PR) perm[t] = t;
+  __syncthreads();
   if (t < PR) {
     const double li = Gs[t][t].x;
     int rank = 0;
@@ -346,8 +348,9 @@ __global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ ba
     const cplx* row = Z + (long long)i * g.ld;
     for (int c = lane; c < g.q_pad; c += 32) acc += cabs2(row[c]);
     acc = warp_sum(acc);
-    if (lane == 0) s2[i] = acc;
+    if (lane == 0) s2[i] = (acc == acc && acc < 1e300) ? acc : 0.0;   // non-finite rows are reported by the NaN guard op, not by a fault here
   }
+  for (int k = t; k < keep; k += blockDim.x) idx[k] = 0;
   __syncthreads();
   double part = 0.0;
   for (int i = t; i < g.p_pad; i += blockDim.x) part += s2[i];

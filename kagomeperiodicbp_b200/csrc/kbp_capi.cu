@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -238,6 +239,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   auto slot_ok = [&](int64_t s) { return s >= -1 && s < c->n_slots; };
   int64_t i = 0;
   int status = KBP_OK;
+  static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
   while (i < n_words) {
     const int64_t op = w[i];
     char where[64];
@@ -352,6 +354,11 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
         BAD("unknown opcode");
     }
     if (c->profile) { cudaEventRecord(pb, c->stream); c->spans.push_back({(int)op, pa, pb}); }
+    if (sync_every) {
+      cudaError_t e_ = cudaStreamSynchronize(c->stream);
+      if (e_ == cudaSuccess) e_ = cudaGetLastError();
+      if (e_ != cudaSuccess) return fail(c, KBP_E_CUDA, std::string("fault detected right after") + where + ": " + cudaGetErrorString(e_));
+    }
   }
 #undef NEED
 #undef BAD

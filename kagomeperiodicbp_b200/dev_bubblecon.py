@@ -15,13 +15,12 @@ import math
 
 import numpy as np
 
-from .dev_mps import DevMPS
+from .dev_mps import DevMPS, Id, absorb_left, absorb_right
 from .program import DT, Program
 
 
-def _id_site(p: Program, DL, Dm, DR) -> DT:
-    n = DL if DL == Dm * DR else DR
-    return p.eye(n, n).reshape(DL, Dm, DR)
+def _id_site(p: Program, DL, Dm, DR):
+    return Id(DL, Dm, DR)          # stays symbolic; see dev_mps.py
 
 
 def fuse_tensor(p: Program, T: DT) -> DT:
@@ -61,17 +60,17 @@ def merge_T(p: Program, mp: DevMPS, A: DT, i0: int, i1: int) -> DevMPS:
             return mp
         if i0 == 0:
             mp.set_lists(As[i1 + 1:], Cs[i1 + 1:])
-            mp.set_site(p.tensordot(A, mp.A[0], ([1], [0])), 0)
+            mp.set_site(absorb_left(p, A, mp.A[0]), 0)
             return mp
         if i1 == mp.N - 1:
             mp.set_lists(As[:i0], Cs[:i0])
-            mp.set_site(p.tensordot(mp.A[i0 - 1], A, ([2], [0])), i0 - 1)
+            mp.set_site(absorb_right(p, mp.A[i0 - 1], A), i0 - 1)
             return mp
         mp.set_lists(As[:i0] + As[i1 + 1:], Cs[:i0] + Cs[i1 + 1:])
         if A.shape[0] < A.shape[1]:
-            mp.set_site(p.tensordot(A, mp.A[i0], ([1], [0])), i0)
+            mp.set_site(absorb_left(p, A, mp.A[i0]), i0)
         else:
-            mp.set_site(p.tensordot(mp.A[i0 - 1], A, ([2], [0])), i0 - 1)
+            mp.set_site(absorb_right(p, mp.A[i0 - 1], A), i0 - 1)
         return mp
     sub = tensor_to_mps_id(p, A, (mp.slot_lognorm, mp.slot_trunc))
     # the end sites of `sub` are [1, DL, DL] and [DR, DR, 1] identities: absorbing them is a reshape
@@ -85,9 +84,9 @@ def swallow_T(p: Program, mp: DevMPS, T: DT, i0, i1, in_legs, out_legs) -> DevMP
     T0 = p.transpose(T, list(in_legs) + list(out_legs))
     nin = len(in_legs)
     out_shape = list(T0.shape[nin:])
-    seg = mp.A[i0]
+    seg = mp.site(i0)
     for i in range(i0 + 1, i1 + 1):
-        seg = p.tensordot(seg, mp.A[i], ([seg.ndim - 1], [0]))
+        seg = p.tensordot(seg, mp.site(i), ([seg.ndim - 1], [0]))
     A = p.tensordot(seg, T0, (list(range(1, 1 + nin)), list(range(nin))))      # [DL, DR, out...]
     if out_legs:
         A = p.transpose(A, [0] + list(range(2, 2 + len(out_shape))) + [1])
@@ -102,7 +101,7 @@ def swallow_ket_T(p: Program, mp: DevMPS, ket_T: DT, i0, i1, in_legs, out_legs) 
     out_shape = list(T0.shape[nin:nin + nout])
     seg = None
     for k, i in enumerate(range(i0, i1 + 1)):
-        a = mp.A[i]
+        a = mp.site(i)
         dk = T0.shape[k]
         assert a.shape[1] == dk * dk, "MPS physical leg must be the fused (ket, bra) pair of the tensor leg"
         a = a.reshape(a.shape[0], dk, dk, a.shape[2])

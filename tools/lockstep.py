@@ -29,7 +29,7 @@ def split_ops(w):
 
 def main():
     D, N, side = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
-    cell = UnitCell.random(2, D, seed=1234)
+    cell = UnitCell.random(2, D, seed=int(os.environ.get("LOCKSTEP_SEED", "1234")))
     tn = bp.KagomeTNRepeatedUnitCell(cell, N)
     tn.connect_uniform_messages()
     comp = bp.compile_side_program(N, 2, D, side, 2 * D * D, bp._msg_shapes(tn.messages), 0.1)
@@ -38,11 +38,20 @@ def main():
     eng.upload(0, comp.pack_inputs([bp._side_inputs(cell, tn.messages, comp)]))
     get = lambda off, n: eng.download(int(off), int(n), chain=0)
     worst = {}
+    wpos = 0
     for k, o in enumerate(split_ops(comp.words)):
         op = int(o[0])
+        wpos_here = wpos; wpos += len(o)
         pre = None
         if op == 5:
             pre = get(o[1], o[2])
+        if wpos_here > int(os.environ.get('LOCKSTEP_MAX_WORD', '1000000000')):
+            break
+        if op == 4 and wpos_here == int(os.environ.get('LOCKSTEP_DUMP_WORD', '-1')):
+            A_, m_, n_ = int(o[1]), int(o[5]), int(o[6])
+            os.makedirs('gpurun_out', exist_ok=True)
+            np.save('gpurun_out/svd_in.npy', get(A_, m_ * n_).reshape(m_, n_))
+            print('dumped svd input at word', wpos_here, flush=True)
         eng.run(np.array(o, dtype=np.int64), soft_errors=(-4,))
         err, what = 0.0, ""
         if op == 1:
@@ -77,12 +86,17 @@ def main():
         elif op == 5:
             x = get(o[1], o[2])
             err = np.abs(x - pre / np.linalg.norm(pre)).max(); what = f"normalize {int(o[2])}"
+        elif op == 10:
+            r, c_ = int(o[2]), int(o[3])
+            err = np.abs(get(o[1], r * c_).reshape(r, c_) - np.eye(r, c_)).max(); what = f"eye {r}x{c_}"
         else:
             continue
+        if not np.isfinite(err):
+            print(f"op #{k} (word {wpos_here}): {what}: NON-FINITE result"); break
         tag = what.split()[0]
         worst[tag] = max(worst.get(tag, 0.0), err)
         if err > 1e-11:
-            print(f"op #{k}: {what}: err {err:.3e}")
+            print(f"op #{k} (word {wpos_here}): {what}: err {err:.3e}", flush=True)
     print("worst per op type:", {k: f"{v:.2e}" for k, v in worst.items()})
 
 

@@ -46,7 +46,8 @@ enum {
   KBP_OP_PERMUTE = 1,        /* dst, src, conj, ndim, dims_src[ndim], perm[ndim] */
   KBP_OP_GEMM = 2,           /* C, A, B, m, n, k, opA, opB      op: 0 N, 1 T, 2 C (conj-transpose), 3 J (conj) */
   KBP_OP_QR = 3,             /* A, Q, R, work, m, n */
-  KBP_OP_SVD = 4,            /* A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc */
+  KBP_OP_SVD = 4,            /* A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, warm (offset of a persistent
+                                kbp_svd_warm_elems buffer or -1) */
   KBP_OP_NORMALIZE = 5,      /* buf, n, slot_lognorm */
   KBP_OP_EMBED = 6,          /* dst, src, alpha_re(bits), alpha_im(bits), d0, d1, d2, s0, s1, s2, sign_slot */
   KBP_OP_ZERO = 7,           /* dst, n */
@@ -61,7 +62,9 @@ void kbp_destroy(kbp_ctx* ctx);
 const char* kbp_last_error(const kbp_ctx* ctx);
 int kbp_device_count(void);
 
-/* arena: nb chains x chain_elems complex128 elements, plus nb x n_slots doubles of scalar slots (zeroed) */
+/* arena: nb chains x chain_elems complex128 elements, plus nb x n_slots doubles of scalar slots (zeroed).
+ * The LAST slot of every chain is reserved by the engine: it counts truncations whose Jacobi iteration did not
+ * converge (the asynchronous counterpart of the KBP_E_SVD_NOCONV return code). */
 int kbp_reserve(kbp_ctx* ctx, int64_t chain_elems, int nb, int n_slots);
 
 /* host <-> device.  `host` holds interleaved complex128.  chain = -1: `host` is [nb][n_elems], one row per chain. */
@@ -78,10 +81,15 @@ int kbp_sync(kbp_ctx* ctx);
 /* workspace sizes (complex128 elements) needed by KBP_OP_SVD / KBP_OP_QR */
 int64_t kbp_svd_work_elems(int64_t m, int64_t n);
 int64_t kbp_qr_work_elems(int64_t m, int64_t n);
+/* persistent buffer in which KBP_OP_SVD keeps its Ritz basis between runs of the same program (0: op never uses one) */
+int64_t kbp_svd_warm_elems(int64_t m, int64_t n, int64_t keep);
 
 /* instrumentation: kernels launched so far; device timing of a region on the context's stream */
 int64_t kbp_launch_count(const kbp_ctx* ctx);
-int64_t kbp_svd_sweeps(const kbp_ctx* ctx);           /* total Jacobi sweeps so far */
+int64_t kbp_svd_sweeps(const kbp_ctx* ctx);           /* total Jacobi sweeps / subspace iterations so far */
+/* out8[1] truncations done by the in-shared-memory Jacobi kernel, [2] by subspace iteration, [3] subspace iterations that
+ * fell back to the exact path, [4] by the block-Jacobi kernel, [5] subspace iterations in total */
+int kbp_svd_counters(const kbp_ctx* ctx, int64_t* out8);
 int kbp_timer_start(kbp_ctx* ctx);
 int kbp_timer_stop_ms(kbp_ctx* ctx, double* ms);       /* synchronises */
 /* per-opcode device time: when enabled, kbp_run brackets every op with CUDA events on the context's stream;

@@ -54,9 +54,24 @@ static SvdGeom svd_geom(int64_t m, int64_t n) {
   return g;
 }
 
+int64_t tsvd_work_elems(int64_t m, int64_t n);
+int tsvd_block(int64_t m, int64_t n, int64_t keep);
+bool svd_small_fits(int64_t m, int64_t n);
+void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
+               int slot_lognorm, int slot_trunc);
+int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                          int nr_bulk, int slot_lognorm, int slot_trunc, int b, int64_t warm);
+void phase_fix(const Arena& a, int64_t Vh, int64_t US, int64_t m, int64_t n, int64_t keep, int us_too);
+
+int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep) {
+  if (svd_small_fits(m, n) || tsvd_block(m, n, keep) == 0) return 0;
+  return n * 112;
+}
+
 int64_t svd_work_elems(int64_t m, int64_t n) {
   SvdGeom g = svd_geom(m, n);
-  return (int64_t)g.p_pad * g.ld;
+  const int64_t jac = (int64_t)g.p_pad * g.ld, sub = tsvd_work_elems(m, n);
+  return jac > sub ? jac : sub;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,9 +429,41 @@ __global__ void fill_kernel(double* p, int n, double v) {
   if (i < n) p[i] = v;
 }
 
+static int svd_truncate_jacobi(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                               int nr_bulk, int slot_lognorm, int slot_trunc);
+
+// Dispatcher: in-smem Jacobi for small matrices, subspace iteration when only a small leading part is kept,
+// full block-Jacobi otherwise / as the exact fallback.  counters: [1] small, [2] subspace ok, [3] subspace fell back,
+// [4] block-Jacobi, [5] subspace iterations.
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                 int nr_bulk, int slot_lognorm, int slot_trunc) {
+                 int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm) {
   if (m == 0 || n == 0) return 0;
+  static const int force = getenv("KBP_SVD_FORCE") ? atoi(getenv("KBP_SVD_FORCE")) : 0;   // 1: block-Jacobi only, 2: no small kernel
+  if (force != 1) {
+    if (force != 2 && svd_small_fits(m, n)) {
+      svd_small(a, A, n, US, Vh, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
+      phase_fix(a, Vh, US, m, n, keep, 1);
+      ++a.counters[1];
+      return 1;
+    }
+    const int b = tsvd_block(m, n, keep);
+    if (b > 0) {
+      const int r = svd_truncate_subspace(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, b, warm);
+      if (r != 0) {
+        if (r > 0) { ++a.counters[2]; a.counters[5] += r; }
+        return r;
+      }
+      ++a.counters[3];
+    }
+  }
+  ++a.counters[4];
+  const int r = svd_truncate_jacobi(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
+  phase_fix(a, Vh, US, m, n, keep, 1);
+  return r;
+}
+
+static int svd_truncate_jacobi(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                               int nr_bulk, int slot_lognorm, int slot_trunc) {
   SvdGeom g = svd_geom(m, n);
   {
     long long total = (long long)g.p_pad * g.ld;

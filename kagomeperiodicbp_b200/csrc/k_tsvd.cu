@@ -1,0 +1,582 @@
+// Rank-`keep` truncated SVD of a LARGE complex128 matrix by block subspace iteration -- the truncation
+// mps.right_canonical asks for (src/libs/bmpslib.py:733-772) keeps chi = 2 D^2 of chi D^2 singular triplets,
+// so the full factorisation numpy computes there is ~10x more work than the answer needs.
+//
+//   Q0 (n x b) pseudo-random, b = 3 keep                              [deterministic hash, no RNG state]
+//   repeat:  W = A Q ;  Y = orth(W) ;  Z = A^H Y ;  Q = orth(Z)        [DMMA ZGEMMs + Cholesky-QR]
+//   Rayleigh-Ritz:  W = A Q = Y R  (Cholesky-QR twice, R = R2 R1, b x b),  R = Ur S Vb^H  by the in-smem
+//   Jacobi kernel (k_svd_small.cu) ->  Vh = Vb_k^H Q^H  (keep x n, orthonormal rows),  US = A Vh^H.
+//   accept iff  max_j || (I - Vh^H Vh) A^H US_j || / (s_j s_1)  <=  TSVD_RES_TOL  and  s_keep / s_1 >= TSVD_MIN_RATIO;
+//   otherwise iterate further, and after TSVD_MAX_ITERS fall back to the full block-Jacobi
+//   SVD (k_svd.cu).  The Ritz vectors j <= keep converge like (s_{b+1} / s_j)^(2 it): the boundary-MPS spectra of
+//   the Kagome block have s_{3 chi} / s_chi ~ 0.05..0.15, i.e. 4-8 iterations for a 1e-13 residual.
+//
+// What is returned is an orthonormal basis Vh of the dominant right singular subspace and US = A Vh^H, so
+// US Vh is exactly the projection of A on that subspace: the same truncated state the reference keeps, in a
+// different (irrelevant) gauge of the kept bond.  The discarded weight is measured directly as
+// ||A - US Vh||_F^2, not as a difference of large numbers.
+#include "kbp_common.cuh"
+#include "kbp_ops.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace kbp {
+
+constexpr int TSVD_BMAX = 112;            // b x b complex must fit one CTA's shared memory (chol + small SVD)
+constexpr double TSVD_RES_TOL = 2e-13;
+constexpr double TSVD_PIVOT_DEAD = 1e-13;  // pivot / diagonal below this: the column is numerically dependent -> dropped
+// Dropped directions carry at most ~3e-7 of a column's norm.  They can only belong to the kept triplets when the
+// spectrum collapses inside the kept part, so a block whose keep-th Ritz value is below this fraction of the first
+// goes to the exact path instead.
+constexpr double TSVD_MIN_RATIO = 3e-6;
+
+static inline int64_t rup8(int64_t x) { return (x + 7) / 8 * 8; }
+
+int tsvd_block(int64_t m, int64_t n, int64_t keep) {
+  static const int factor_x10 = getenv("KBP_TSVD_FACTOR_X10") ? atoi(getenv("KBP_TSVD_FACTOR_X10")) : 30;
+  const int64_t p = m < n ? m : n;
+  int64_t b = rup8(keep * factor_x10 / 10);
+  if (b > TSVD_BMAX) b = TSVD_BMAX;
+  if (b < keep + 8 || b * 100 > p * 65) return 0;     // not worth it / not applicable
+  return (int)b;
+}
+
+int64_t tsvd_work_elems(int64_t m, int64_t n) {
+  const int64_t q = m < n ? n : m, b = TSVD_BMAX;
+  return 4 * rup8(q) * b + 16 * b * b + m * n + 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void tsvd_randq_kernel(cplx* __restrict__ base, long long chain_stride, long long Q_, long long total) {
+  cplx* Q = base + (long long)blockIdx.y * chain_stride + Q_;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long h = splitmix((unsigned long long)e * 2 + 12345), h2 = splitmix(h);
+    Q[e] = cmake((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5, (double)(h2 >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA per chain: Cholesky G = R^H R of a b x b Hermitian Gram matrix (given as `nsplit` partial sums) in
+// shared memory, then Rinv = R^{-1}.  Blocked by panels of 16: the diagonal block is factored and inverted by one
+// warp with warp-level synchronisation only, the panel rows and the trailing update are block-parallel (3 barriers
+// per panel instead of 3 per column), and the off-diagonal blocks of the inverse follow level by level.  R stays in
+// the upper triangle, R^{-1} is built transposed in the strict lower triangle, its diagonal in dinv.
+// Columns whose pivot is below TSVD_PIVOT_DEAD of their diagonal are dropped (row of R, column of Rinv = 0: the
+// orthonormalised block gets a zero column there).  stat[chain] = min over live columns of pivot/diagonal.
+constexpr int CNB = 16;
+
+__global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit,
+                                                        long long R_, long long Rinv_, int b, double* __restrict__ stat) {
+  extern __shared__ __align__(16) unsigned char ch_raw[];
+  cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x b
+  double* diag0 = reinterpret_cast<double*>(S + (size_t)b * b);    // original diagonal
+  double* dinv = diag0 + b;                                        // 1 / R_jj (0 for dropped columns)
+  __shared__ double sh_min;
+  cplx* cb = base + (long long)blockIdx.x * chain_stride;
+  const cplx* G = cb + G_;
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, w = t >> 5;
+  for (int e = t; e < b * b; e += nt) {
+    cplx v = G[e];
+    for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, G[(long long)sp * b * b + e]);
+    S[e] = v;
+  }
+  __syncthreads();
+  for (int i = t; i < b; i += nt) diag0[i] = S[i * b + i].x;
+  if (t == 0) sh_min = 1.0;
+  __syncthreads();
+
+  for (int p0 = 0; p0 < b; p0 += CNB) {
+    const int p1 = p0 + CNB < b ? p0 + CNB : b, pw = p1 - p0;
+    // ---- phase A (warp 0): factor the diagonal block, then invert it.  Lane -> (row i = lane / 2, 8 columns): fixed
+    //      mapping, no index arithmetic in the 16 dependent pivot steps
+    if (w == 0) {
+      double mn = 1.0;
+      const int li = p0 + (lane >> 1), lc0 = p0 + (lane & 1) * 8;
+      for (int j = p0; j < p1; ++j) {
+        const double d = S[j * b + j].x, d0 = diag0[j];
+        const bool live = d0 > 0.0 && d > TSVD_PIVOT_DEAD * d0;      // NaN -> dropped
+        const double ip = live ? rsqrt(d) : 0.0;
+        if (live) mn = fmin(mn, d / d0);
+        __syncwarp();
+        if (li == j) {                                            // the two lanes of row j scale it
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int l = lc0 + u;
+            if (l > j && l < p1) S[j * b + l] = cscale(S[j * b + l], ip);
+            else if (l == j) { S[j * b + j] = cmake(live ? d * ip : 0.0, 0.0); dinv[j] = ip; }
+          }
+        }
+        __syncwarp();
+        if (li > j && li < p1) {
+          const cplx rji = S[j * b + li];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int l = lc0 + u;
+            if (l >= li && l < p1) {
+              const cplx v = ccmul(rji, S[j * b + l]);
+              cplx x = S[li * b + l];
+              x.x -= v.x; x.y -= v.y;
+              if (l == li) x.y = 0.0;
+              S[li * b + l] = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) sh_min = fmin(sh_min, mn);
+      // inverse of the diagonal block: lanes (2c, 2c+1) own column l = p0 + c and split the sums;  X[i][l] (i < l) is
+      // stored at S[l][i]
+      {
+        const int l = p0 + (lane >> 1), half = lane & 1;
+        const bool act = l < p1;
+        const double xll = act ? dinv[l] : 0.0;
+        for (int i = p1 - 2; i >= p0; --i) {
+          cplx acc = cmake(0.0, 0.0);
+          if (act && i < l) {
+            if (half == 0) acc = cscale(S[i * b + l], xll);              // R[i][l] x_ll
+            for (int r = i + 1 + half; r < l; r += 2) acc = cfma(S[i * b + r], S[l * b + r], acc);
+          }
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+          if (act && i < l && half == 0) S[l * b + i] = cscale(acc, -dinv[i]);
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    const int rem = b - p1;
+    if (rem > 0) {
+      // ---- phase B: panel rows  R[r][l] = sum_{r' <= r} conj(X[r'][r]) S[r'][l],  l >= p1  (registers, then write)
+      cplx outv[2];
+      const int nel = pw * rem;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = t + u * 1024;
+        outv[u] = cmake(0.0, 0.0);
+        if (e < nel) {
+          const int r = p0 + e / rem, l = p1 + e % rem;
+          cplx acc = cscale(S[r * b + l], dinv[r]);
+          for (int rp = p0; rp < r; ++rp) acc = cadd(acc, ccmul(S[r * b + rp], S[rp * b + l]));
+          outv[u] = acc;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = t + u * 1024;
+        if (e < nel) S[(p0 + e / rem) * b + p1 + e % rem] = outv[u];
+      }
+      __syncthreads();
+      // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
+      for (int e = t; e < rem * rem; e += nt) {
+        const int i = p1 + e / rem, l = p1 + e % rem;
+        if (l >= i) {
+          cplx x = S[i * b + l];
+          for (int r = p0; r < p1; ++r) {
+            const cplx v = ccmul(S[r * b + i], S[r * b + l]);
+            x.x -= v.x; x.y -= v.y;
+          }
+          if (l == i) x.y = 0.0;
+          S[i * b + l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (R_ >= 0) {
+    cplx* R = cb + R_;
+    for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[e] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  // ---- off-diagonal blocks of the inverse, level d = block column - block row:
+  //      X_pq = -X_pp (sum_{p < r <= q} R_pr X_rq);   X[j][l] (j < l) lives at S[l][j], X[l][l] = dinv[l]
+  const int nblk = (b + CNB - 1) / CNB;
+  for (int d = 1; d < nblk; ++d) {
+    const int nel = (nblk - d) * CNB * CNB;
+    cplx tv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + u * 1024;
+      tv[u] = cmake(0.0, 0.0);
+      if (e < nel) {
+        const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
+        if (l < b) {
+          cplx acc = cscale(S[ip * b + l], dinv[l]);               // j == l
+          for (int j = (pb + 1) * CNB; j < l; ++j) acc = cfma(S[ip * b + j], S[l * b + j], acc);
+          tv[u] = acc;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + u * 1024;
+      if (e < nel) {
+        const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
+        if (l < b) S[l * b + ip] = tv[u];                           // T, parked where X_pq will go
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + u * 1024;
+      tv[u] = cmake(0.0, 0.0);
+      if (e < nel) {
+        const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
+        if (l < b) {
+          cplx acc = cscale(S[l * b + i], dinv[i]);                 // i' == i
+          for (int ip = i + 1; ip < (pb + 1) * CNB; ++ip) acc = cfma(S[ip * b + i], S[l * b + ip], acc);
+          tv[u] = cmake(-acc.x, -acc.y);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + u * 1024;
+      if (e < nel) {
+        const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
+        if (l < b) S[l * b + i] = tv[u];
+      }
+    }
+    __syncthreads();
+  }
+  cplx* Rinv = cb + Rinv_;
+  for (int e = t; e < b * b; e += nt) {
+    const int i = e / b, l = e % b;
+    Rinv[e] = i < l ? S[l * b + i] : (i == l ? cmake(dinv[i], 0.0) : cmake(0.0, 0.0));
+  }
+  if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], sh_min);
+}
+
+// How far span(Vh) is from an invariant subspace of A^H A, and the discarded weight, in two launches.
+//   C = US^H A (keep x n),  T = C Vh^H = US^H US (keep x keep, T_jj = s_j^2),  TV = T Vh,  P = US Vh (m x n)
+//   stage 1 (grid NPART x nb): partial sums of  r_j = ||C_j - TV_j||^2  (rows j),  ||A||_F^2  and  ||A - P||_F^2
+//   stage 2 (one CTA per chain): out[0] = max_j sqrt(r_j / (s_j^2 s_1^2)), out[1] = min_j s_j / s_1, out[2] = ||A - P||^2 / ||A||^2
+// Only the part of the residual OUTSIDE span(Vh) counts (C - T Vh): the part inside is a change of gauge of the kept
+// bond, and it is also where the rounding of US = A Vh^H (absolute error eps s_1, amplified by A^H to eps s_1^2) lands,
+// which would otherwise put a floor of eps s_1 / s_j under the test.
+constexpr int NPART = 32;
+constexpr int PART_STRIDE = 160;     // doubles per (chain, part): keep <= 128 row sums + 2 norms
+
+__global__ void __launch_bounds__(256) tsvd_check1_kernel(const cplx* __restrict__ base, long long chain_stride, long long C_, long long TV_,
+                                                          long long A_, long long P_, int m, int n, int keep, double* __restrict__ part) {
+  __shared__ double red[34];
+  const cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const cplx* C = cb + C_;
+  const cplx* TV = cb + TV_;
+  const cplx* A = cb + A_;
+  const cplx* P = cb + P_;
+  double* out = part + ((long long)blockIdx.y * NPART + blockIdx.x) * PART_STRIDE;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  // rows of C - TV: part x owns a column range
+  const int c0 = (int)((long long)n * blockIdx.x / NPART), c1 = (int)((long long)n * (blockIdx.x + 1) / NPART);
+  for (int j = w; j < keep; j += 8) {
+    double acc = 0.0;
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const cplx x = C[(long long)j * n + c], y = TV[(long long)j * n + c];
+      const double dx = x.x - y.x, dy = x.y - y.y;
+      acc += dx * dx + dy * dy;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[j] = acc;
+  }
+  const long long mn = (long long)m * n;
+  const long long e0 = mn * blockIdx.x / NPART, e1 = mn * (blockIdx.x + 1) / NPART;
+  double fa = 0.0, fd = 0.0;
+  for (long long e = e0 + t; e < e1; e += 256) {
+    const cplx x = A[e], y = P[e];
+    fa += cabs2(x);
+    const double dx = x.x - y.x, dy = x.y - y.y;
+    fd += dx * dx + dy * dy;
+  }
+  fa = block_sum(fa, red);
+  fd = block_sum(fd, red);
+  if (t == 0) { out[keep] = fa; out[keep + 1] = fd; }
+}
+
+__global__ void __launch_bounds__(128) tsvd_check2_kernel(const cplx* __restrict__ base, long long chain_stride, long long T_, int keep,
+                                                          const double* __restrict__ part, double* __restrict__ resid, double* __restrict__ ratio,
+                                                          double* __restrict__ discfrac, double* __restrict__ norms) {
+  __shared__ double s2[128], r2[128];
+  __shared__ double sh[2];
+  const cplx* T = base + (long long)blockIdx.x * chain_stride + T_;
+  const double* pp = part + (long long)blockIdx.x * NPART * PART_STRIDE;
+  const int t = threadIdx.x;
+  if (t < keep) {
+    double acc = 0.0;
+    for (int x = 0; x < NPART; ++x) acc += pp[x * PART_STRIDE + t];
+    r2[t] = acc;
+    s2[t] = T[(long long)t * keep + t].x;
+  }
+  if (t < 2) {
+    double acc = 0.0;
+    for (int x = 0; x < NPART; ++x) acc += pp[x * PART_STRIDE + keep + t];
+    sh[t] = acc;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double smax = 0.0;
+    for (int j = 0; j < keep; ++j) smax = fmax(smax, s2[j]);
+    double worst = 0.0, smin = smax;
+    for (int j = 0; j < keep; ++j) {
+      if (s2[j] > 1e-30 * smax) worst = fmax(worst, sqrt(r2[j] / (s2[j] * smax)));
+      smin = fmin(smin, s2[j]);
+    }
+    if (!(worst == worst)) worst = 1e300;
+    resid[blockIdx.x] = worst;
+    ratio[blockIdx.x] = (smax > 0.0 && smin > 0.0) ? sqrt(smin / smax) : 0.0;
+    discfrac[blockIdx.x] = sh[0] > 0.0 ? sh[1] / sh[0] : 0.0;
+    norms[2 * blockIdx.x] = sh[0];
+    norms[2 * blockIdx.x + 1] = sh[1];
+  }
+}
+
+// One CTA per chain: scale US by 1 / ||A||_F (nr_bulk) and update the slots from the norms check2 left behind.
+__global__ void __launch_bounds__(1024) tsvd_finalize_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots, int n_slots,
+                                                             long long US_, long long mk, int nr_bulk, int slot_lognorm, int slot_trunc,
+                                                             const double* __restrict__ norms) {
+  cplx* US = base + (long long)blockIdx.x * chain_stride + US_;
+  const double fro2 = norms[2 * blockIdx.x], disc = norms[2 * blockIdx.x + 1];
+  const double frob = sqrt(fro2);
+  if (nr_bulk && frob > 0.0) {
+    const double sc = 1.0 / frob;
+    for (long long e = threadIdx.x; e < mk; e += blockDim.x) US[e] = cscale(US[e], sc);
+  }
+  if (threadIdx.x == 0) {
+    double* sl = slots + (long long)blockIdx.x * n_slots;
+    if (nr_bulk && slot_lognorm >= 0 && frob > 0.0) sl[slot_lognorm] += log(frob);
+    if (slot_trunc >= 0 && fro2 > 0.0) sl[slot_trunc] += sqrt(disc / fro2);
+  }
+}
+
+// Canonical phase of the kept right singular vectors: row k of Vh (keep x n) is multiplied by conj(phase) of its
+// largest-magnitude entry (first one on ties), so that entry becomes real positive; with us_too the column k of US
+// (m x keep) gets the phase back, leaving US Vh unchanged.  This pins the gauge of the truncated bond: the sites of
+// the next BP iteration are then continuous functions of the messages, which is what lets the subspace iteration be
+// warm-started from the previous run's Ritz basis.  One CTA per chain, one warp per row.
+__global__ void __launch_bounds__(1024) phase_fix_kernel(cplx* __restrict__ base, long long chain_stride, long long Vh_, long long US_, int m, int n,
+                                                         int keep, int us_too) {
+  cplx* Vh = base + (long long)blockIdx.x * chain_stride + Vh_;
+  cplx* US = base + (long long)blockIdx.x * chain_stride + US_;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = w; k < keep; k += nw) {
+    cplx* row = Vh + (long long)k * n;
+    double best = -1.0;
+    int bi = 0;
+    for (int c = lane; c < n; c += 32) {
+      const double v = cabs2(row[c]);
+      if (v > best) { best = v; bi = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (!(best > 0.0)) continue;
+    const cplx p = row[bi];
+    const double inv = rsqrt(best);
+    const cplx ph = cmake(p.x * inv, p.y * inv);            // unit phase of the pivot entry
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) {
+      cplx v = cmulc(row[c], ph);                           // * conj(ph)
+      if (c == bi) v.y = 0.0;
+      row[c] = v;
+    }
+    if (us_too)
+      for (int r = lane; r < m; r += 32) US[(long long)r * keep + k] = cmul(US[(long long)r * keep + k], ph);
+  }
+}
+
+void phase_fix(const Arena& a, int64_t Vh, int64_t US, int64_t m, int64_t n, int64_t keep, int us_too) {
+  phase_fix_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, Vh, US, (int)m, (int)n, (int)keep, us_too);
+  ++*a.launches;
+}
+
+__global__ void tsvd_fill_kernel(double* p, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
+               int slot_lognorm, int slot_trunc);
+
+// Y (rows x b) <- Y Rinv with G = Y^H Y = R^H R.  `T` is a rows x b scratch; returns the buffer holding the result
+// (Y and T swap roles).  R_out >= 0: also store R.  The Gram matrix is accumulated as GRAM_SPLIT partial sums over
+// row ranges (more CTAs on a product whose output is only b x b) which the Cholesky kernel adds up.
+constexpr int GRAM_SPLIT = 4;
+
+static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Rinv, int64_t R_out, int64_t rows, int b, double* stat) {
+  const int split = rows >= 256 ? GRAM_SPLIT : 1;
+  gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
+  const size_t smem = sizeof(double2) * (size_t)b * b + 2 * sizeof(double) * (size_t)b + 32;
+  chol_inv_kernel<<<a.nb, 1024, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Rinv, b, stat);
+  ++*a.launches;
+  if (T >= 0) gemm(a, T, Y, Rinv, rows, b, b, OP_N, OP_N);      // T < 0: only R is wanted
+  return T;
+}
+
+// returns iterations used (> 0) on success, 0 if the caller must fall back to the full Jacobi SVD, < 0 on CUDA failure
+//
+// Two kinds of iteration.  SAFE (cold start, Q arbitrary): W = A Q, Y = orth(W), Z = A^H Y, Q = orth(Z).  FAST (Q holds
+// approximate Ritz vectors in decreasing order -- after the first Rayleigh-Ritz step, or from the previous run of the same
+// op): the columns of A Q and of A^H A Q are then nearly orthogonal, their Gram matrices are diagonally dominant after
+// scaling, and ONE Cholesky-QR of Z = A^H (A Q) per iteration is as accurate as the safe sequence (the Cholesky kernel
+// reports its smallest pivot / diagonal; a result built on a pivot ratio below TSVD_PIVOT_TRUST is not accepted).
+constexpr double TSVD_PIVOT_TRUST = 1e-3;
+
+int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                          int nr_bulk, int slot_lognorm, int slot_trunc, int b, int64_t warm) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    attr_set = true;
+  }
+  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
+  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 2;
+  static const int it_warm = getenv("KBP_TSVD_ITWARM") ? atoi(getenv("KBP_TSVD_ITWARM")) : 2;
+  static const int it_step = getenv("KBP_TSVD_ITSTEP") ? atoi(getenv("KBP_TSVD_ITSTEP")) : 3;
+  static const int it_max = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 24;
+  // warm start from the previous run's Ritz basis is opt-in: across BP iterations the message tensors keep changing gauge
+  // in their (physically irrelevant) near-null directions, which makes the stored basis stale more often than not
+  static const bool no_warm = getenv("KBP_TSVD_WARM") == nullptr || atoi(getenv("KBP_TSVD_WARM")) == 0;
+  const int64_t q = m < n ? n : m, qp = rup8(q), bb = (int64_t)b * b;
+  // workspace carve-up (complex128 elements)
+  int64_t o = work;
+  int64_t buf[4];                     // four q x b panels: Q, W, scratch, check product
+  for (int i = 0; i < 4; ++i) { buf[i] = o; o += qp * b; }
+  const int64_t Gp = o; o += GRAM_SPLIT * bb;
+  const int64_t Ri = o; o += bb;
+  const int64_t R1 = o; o += bb;
+  const int64_t R2 = o; o += bb;
+  const int64_t Rm = o; o += bb;
+  const int64_t USs = o; o += bb;    // b x b (unused output of the small SVD)
+  const int64_t Vbs = o; o += bb;    // b x b: all Ritz vectors, rows sorted by singular value
+  const int64_t Tk = o; o += bb;     // keep x keep
+  const int64_t Pb = o;              // m x n: P = US Vh
+  double* stat = a.svd_off;          // [nb] min pivot ratio
+  double* resid = a.svd_off + a.nb;
+  double* ratio = a.svd_off + 2 * a.nb;
+  double* discf = a.svd_off + 3 * a.nb;
+  double* norms = a.svd_off + 4 * a.nb;            // [2 nb]
+  double* part = a.svd_off + 6 * a.nb;             // [nb][NPART][PART_STRIDE]
+  if (keep > 128) return 0;
+
+  // panel bookkeeping: Qb = current basis, the rest are free
+  int64_t Qb, f0 = buf[1], f1 = buf[2], f2 = buf[3];
+  bool ordered = false;
+  if (warm >= 0 && !no_warm) {
+    auto it = a.warm->find((long long)warm);
+    ordered = it != a.warm->end() && it->second == b;
+  }
+  const bool is_warm = ordered;
+  if (ordered) {
+    Qb = warm;                       // Ritz basis of the previous run of this op (n x b, orthonormal columns); read only
+  } else {
+    Qb = buf[0];
+    const long long total = (long long)n * b;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 4) gx = 148 * 4;
+    tsvd_randq_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, Qb, total);
+    ++*a.launches;
+  }
+  // after `Qb = newbuf`, the old basis panel becomes free unless it is the persistent warm buffer
+  auto replace_q = [&](int64_t nq) {
+    const int64_t old = Qb;
+    Qb = nq;
+    if (nq == f0) f0 = old; else if (nq == f1) f1 = old; else f2 = old;
+    if (old == warm) { if (f0 == warm) f0 = buf[0]; else if (f1 == warm) f1 = buf[0]; else if (f2 == warm) f2 = buf[0]; }
+  };
+  int done = 0, target = ordered ? it_warm : it_cold;
+  if (target < 1) target = 1;
+  while (true) {
+    tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
+    ++*a.launches;
+    const bool rr_ordered = ordered;
+    for (; done < target; ++done) {
+      gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
+      if (!ordered) {
+        cholqr_pass(a, f0, f1, Gp, Ri, -1, m, b, stat);               // Y = orth(W)      -> f1
+        gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                      // Z = A^H Y        -> f0
+        cholqr_pass(a, f0, f1, Gp, Ri, -1, n, b, stat);               // orth(Z)          -> f1
+        if (done + 1 == target) { cholqr_pass(a, f1, f0, Gp, Ri, -1, n, b, stat); replace_q(f0); }   // twice on the last one
+        else replace_q(f1);
+      } else {
+        gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
+        cholqr_pass(a, f1, f0, Gp, Ri, -1, n, b, stat);               // Q = orth(Z)      -> f0
+        replace_q(f0);
+      }
+    }
+    // ---- Rayleigh-Ritz on span(Q)
+    gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q -> f0
+    int64_t Rsmall;
+    if (rr_ordered) {
+      cholqr_pass(a, f0, -1, Gp, Ri, R1, m, b, stat);                 // W = Y R1
+      Rsmall = R1;
+    } else {
+      cholqr_pass(a, f0, f1, Gp, Ri, R1, m, b, stat);
+      cholqr_pass(a, f1, -1, Gp, Ri, R2, m, b, stat);
+      gemm(a, Rm, R2, R1, b, b, b, OP_N, OP_N);                       // W = Y (R2 R1)
+      Rsmall = Rm;
+    }
+    svd_small(a, Rsmall, b, USs, Vbs, b, b, b, 0, -1, -1);            // Vbs = Vb^H (b x b), rows by decreasing singular value
+    gemm(a, Vh, Vbs, Qb, keep, n, b, OP_N, OP_C);                     // Vh = Vb_k^H Q^H
+    phase_fix(a, Vh, US, m, n, keep, 0);                              // canonical gauge of the kept bond
+    gemm(a, US, A, Vh, m, keep, n, OP_N, OP_C);                       // US = A Vh^H
+    gemm(a, f0, US, A, keep, n, m, OP_C, OP_N);                       // C = US^H A        -> f0
+    gemm(a, Tk, f0, Vh, keep, keep, n, OP_N, OP_C);                   // T = C Vh^H
+    gemm(a, f1, Tk, Vh, keep, n, keep, OP_N, OP_N);                   // TV = T Vh         -> f1
+    gemm(a, Pb, US, Vh, m, n, keep, OP_N, OP_N);                      // P = US Vh
+    tsvd_check1_kernel<<<dim3(NPART, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, f0, f1, A, Pb, (int)m, (int)n, (int)keep, part);
+    tsvd_check2_kernel<<<a.nb, 128, 0, a.stream>>>(a.base, a.chain_stride, Tk, (int)keep, part, resid, ratio, discf, norms);
+    *a.launches += 2;
+    // one host round trip: [stat | resid | ratio | discfrac] are contiguous in svd_off
+    cudaMemcpyAsync(a.svd_off_host, a.svd_off, sizeof(double) * 4 * a.nb, cudaMemcpyDeviceToHost, a.stream);
+    if (cudaStreamSynchronize(a.stream) != cudaSuccess) return -1;
+    double worst = 0.0, minpiv = 1.0, minratio = 1.0, maxdisc = 0.0;
+    for (int c = 0; c < a.nb; ++c) {
+      const double pv = a.svd_off_host[c], rs = a.svd_off_host[a.nb + c], ra = a.svd_off_host[2 * a.nb + c], df = a.svd_off_host[3 * a.nb + c];
+      if (!(rs == rs) || !(ra == ra) || !(df == df)) { worst = 1e300; continue; }
+      if (pv < minpiv) minpiv = pv;
+      if (rs > worst) worst = rs;
+      if (ra < minratio) minratio = ra;
+      if (df > maxdisc) maxdisc = df;
+    }
+    if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d%s%s] it %d resid %.3e s_k/s_1 %.3e min pivot %.3e disc %.3e\n", (long long)m, (long long)n,
+                       (long long)keep, b, is_warm ? " warm" : "", rr_ordered ? " fast" : "", done, worst, minratio, minpiv, maxdisc);
+    // a spectrum that collapses inside the kept part: fine if nothing measurable is discarded (rank <= keep), else exact
+    // path.  A fast round whose Cholesky pivots were small says nothing either way: it is redone with safe iterations.
+    const bool trusted = !rr_ordered || minpiv >= TSVD_PIVOT_TRUST;
+    const bool collapse = trusted && minratio < TSVD_MIN_RATIO && maxdisc > 1e-24;
+    if (!collapse && trusted && worst <= TSVD_RES_TOL) break;
+    if (collapse || done >= it_max) {
+      if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld] FALLBACK after %d iterations: resid %.3e s_k/s_1 %.3e\n", (long long)m, (long long)n, done, worst, minratio);
+      if (warm >= 0) a.warm->erase((long long)warm);
+      return 0;
+    }
+    // continue from the Ritz basis Q Vb (ordered) -- unless the fast path just proved untrustworthy
+    gemm(a, f2, Qb, Vbs, n, b, b, OP_N, OP_C);
+    replace_q(f2);
+    ordered = trusted;
+    target = done + (done < 12 ? it_step : 2 * it_step);
+    if (target > it_max) target = it_max;
+  }
+  if (warm >= 0 && !no_warm) {
+    gemm(a, warm, Qb, Vbs, n, b, b, OP_N, OP_C);                      // Ritz basis Q Vb for the next run (Qb != warm here)
+    (*a.warm)[(long long)warm] = b;
+  }
+  tsvd_finalize_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, US, m * keep, nr_bulk, slot_lognorm, slot_trunc, norms);
+  ++*a.launches;
+  return done > 0 ? done : 1;
+}
+
+}  // namespace kbp

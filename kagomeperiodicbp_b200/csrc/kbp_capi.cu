@@ -23,6 +23,8 @@ struct kbp_ctx {
   double* svd_off_host = nullptr;
   int64_t launches = 0;
   int64_t svd_sweeps = 0;
+  int64_t counters[8] = {0};
+  std::unordered_map<long long, int> warm;
   bool profile = false;
   struct Span { int op; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -99,11 +101,12 @@ int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
     free_arena(c);
     CU(c, cudaMalloc(&c->arena, sizeof(double2) * (size_t)chain_elems * nb));
     CU(c, cudaMalloc(&c->slots, sizeof(double) * (size_t)nb * n_slots));
-    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * 3 * nb));
-    CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * nb));
+    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)(6 + 32 * 160) * nb));
+    CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * 4 * nb));
     c->chain_elems = chain_elems; c->nb = nb; c->n_slots = n_slots;
   }
   CU(c, cudaMemsetAsync(c->slots, 0, sizeof(double) * (size_t)nb * n_slots, c->stream));
+  c->warm.clear();      // a new program layout: no warm-start buffer holds a basis any more
   return KBP_OK;
 }
 
@@ -180,8 +183,14 @@ int64_t kbp_qr_work_elems(int64_t m, int64_t n) {
   int64_t k = m < n ? m : n;
   return m * n + m * k + k + 8;
 }
+int64_t kbp_svd_warm_elems(int64_t m, int64_t n, int64_t keep) { return kbp::svd_warm_elems(m, n, keep); }
 int64_t kbp_launch_count(const kbp_ctx* c) { return c ? c->launches : 0; }
 int64_t kbp_svd_sweeps(const kbp_ctx* c) { return c ? c->svd_sweeps : 0; }
+int kbp_svd_counters(const kbp_ctx* c, int64_t* out8) {
+  if (!c || !out8) return KBP_E_ARG;
+  for (int i = 0; i < 8; ++i) out8[i] = c->counters[i];
+  return KBP_OK;
+}
 
 int kbp_timer_start(kbp_ctx* c) {
   if (!c) return KBP_E_ARG;
@@ -233,7 +242,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
-  a.stream = c->stream; a.launches = &c->launches; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.stream = c->stream; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };
   auto slot_ok = [&](int64_t s) { return s >= -1 && s < c->n_slots; };
@@ -289,18 +298,19 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
         break;
       }
       case KBP_OP_SVD: {
-        NEED(10);
+        NEED(11);
         const int64_t A = w[i + 1], US = w[i + 2], Vh = w[i + 3], wk = w[i + 4], m = w[i + 5], n = w[i + 6], keep = w[i + 7];
-        const int64_t nrb = w[i + 8], s0 = w[i + 9], s1 = w[i + 10];
+        const int64_t nrb = w[i + 8], s0 = w[i + 9], s1 = w[i + 10], warm = w[i + 11];
         if (m <= 0 || n <= 0 || keep <= 0 || keep > (m < n ? m : n) || !slot_ok(s0) || !slot_ok(s1)) BAD("svd: bad argument");
         if (!in_arena(A, m * n) || !in_arena(US, m * keep) || !in_arena(Vh, keep * n) || !in_arena(wk, kbp::svd_work_elems(m, n)))
           BAD("svd: buffer out of arena");
-        int sw = kbp::svd_truncate(a, A, US, Vh, wk, m, n, keep, (int)nrb, (int)s0, (int)s1);
+        if (warm >= 0 && !in_arena(warm, kbp::svd_warm_elems(m, n, keep))) BAD("svd: warm-start buffer out of arena");
+        int sw = kbp::svd_truncate(a, A, US, Vh, wk, m, n, keep, (int)nrb, (int)s0, (int)s1, warm);
         if (sw == -1) return fail(c, KBP_E_CUDA, std::string("svd: ") + cudaGetErrorString(cudaGetLastError()) + where);
         if (sw == -2) { status = KBP_E_NONFINITE; c->err = std::string("svd: non-finite input") + where; }
         else if (sw == -3) { if (status == KBP_OK) { status = KBP_E_SVD_NOCONV; c->err = std::string("svd: Jacobi did not converge") + where; } }
         else c->svd_sweeps += sw;
-        i += 11;
+        i += 12;
         break;
       }
       case KBP_OP_NORMALIZE: {

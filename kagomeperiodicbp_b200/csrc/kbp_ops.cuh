@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <unordered_map>
+
 namespace kbp {
 
 struct Arena {
@@ -16,9 +18,12 @@ struct Arena {
   int nb;
   cudaStream_t stream;
   int64_t* launches;      // host counter of kernel launches
+  int64_t* counters;      // host counters [8]: see svd_truncate
+  std::unordered_map<long long, int>* warm;   // warm-start buffers that hold a valid Ritz basis: offset -> block size
   // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
-  double* svd_off;        // device: [3][nb]  (off current / previous sweep, ||A||_F^2)
-  double* svd_off_host;   // pinned host mirror: [nb]
+  double* svd_off;        // device: [6 + 32*160][nb]  (Jacobi: off current / previous sweep, ||A||_F^2; subspace: pivot, residual,
+                          // ratio, discarded fraction, norms, partial sums of the check kernels)
+  double* svd_off_host;   // pinned host mirror: [4][nb]
 };
 
 enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };   // as-is, transpose, conj-transpose, conj
@@ -33,7 +38,10 @@ void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m
 // slot_lognorm += ln ||A||_F (if nr_bulk); slot_trunc += sqrt(sum_discarded s^2 / sum s^2).
 // work: see svd_work_elems().  Returns the number of Jacobi sweeps used (max over chains), <0 on failure.
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                 int nr_bulk, int slot_lognorm, int slot_trunc);
+                 int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm);
+int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep);
+// C partial sums side by side (C + s*m*n, s < ksplit), each over a contiguous range of k
+void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit);
 int64_t svd_work_elems(int64_t m, int64_t n);
 // buf /= ||buf||_F ; slot += ln ||buf||_F
 void normalize(const Arena& a, int64_t buf, int64_t n, int slot_lognorm);

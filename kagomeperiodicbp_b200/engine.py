@@ -19,7 +19,7 @@ E_SVD_NOCONV, E_NONFINITE = -4, -5
 EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
-    "kbp_qr_work_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_timer_start", "kbp_timer_stop_ms",
+    "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
     "kbp_profile_enable", "kbp_profile_read",
 ]
 
@@ -62,8 +62,10 @@ def load_library():
         lib.kbp_sync.argtypes = [P]; lib.kbp_sync.restype = I
         lib.kbp_svd_work_elems.argtypes = [L, L]; lib.kbp_svd_work_elems.restype = L
         lib.kbp_qr_work_elems.argtypes = [L, L]; lib.kbp_qr_work_elems.restype = L
+        lib.kbp_svd_warm_elems.argtypes = [L, L, L]; lib.kbp_svd_warm_elems.restype = L
         lib.kbp_launch_count.argtypes = [P]; lib.kbp_launch_count.restype = L
         lib.kbp_svd_sweeps.argtypes = [P]; lib.kbp_svd_sweeps.restype = L
+        lib.kbp_svd_counters.argtypes = [P, P]; lib.kbp_svd_counters.restype = I
         lib.kbp_timer_start.argtypes = [P]; lib.kbp_timer_start.restype = I
         lib.kbp_timer_stop_ms.argtypes = [P, ctypes.POINTER(D)]; lib.kbp_timer_stop_ms.restype = I
         lib.kbp_profile_enable.argtypes = [P, I]; lib.kbp_profile_enable.restype = I
@@ -77,7 +79,21 @@ def svd_work_elems(m: int, n: int) -> int:
     p, q = (n, m) if m >= n else (m, n)
     p_pad = (p + 31) // 32 * 32
     q_pad = (q + 7) // 8 * 8
-    return p_pad * (q_pad + p_pad)
+    jacobi = p_pad * (q_pad + p_pad)
+    subspace = 4 * q_pad * 112 + 16 * 112 * 112 + m * n + 64      # k_tsvd.cu: tsvd_work_elems
+    return max(jacobi, subspace)
+
+
+def svd_warm_elems(m: int, n: int, keep: int) -> int:
+    """size of the persistent Ritz-basis buffer of one truncation (0: the op never takes the subspace path).
+    Mirrors kbp_svd_warm_elems / tsvd_block in k_tsvd.cu."""
+    p = min(m, n)
+    if m <= n and m <= 128 and p * max(m, n) * 16 + p * 12 + 64 <= 225 * 1024:
+        return 0                                  # in-shared-memory Jacobi
+    b = min(112, (3 * keep + 7) // 8 * 8)
+    if b < keep + 8 or b * 100 > p * 65:
+        return 0
+    return n * 112
 
 
 def qr_work_elems(m: int, n: int) -> int:
@@ -160,6 +176,13 @@ class Engine:
 
     def svd_sweeps(self) -> int:
         return int(self.lib.kbp_svd_sweeps(self.h))
+
+    def svd_counters(self) -> dict:
+        """how the truncations were executed so far: in-smem Jacobi / subspace iteration / its fallbacks / block-Jacobi."""
+        out = np.zeros(8, dtype=np.int64)
+        self._check(self.lib.kbp_svd_counters(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return {"small": int(out[1]), "subspace": int(out[2]), "subspace_fallback": int(out[3]), "block_jacobi": int(out[4]),
+                "subspace_iterations": int(out[5])}
 
     def profile_enable(self, on: bool):
         self._check(self.lib.kbp_profile_enable(self.h, 1 if on else 0))

@@ -11,7 +11,7 @@ import threading
 
 import numpy as np
 
-from .engine import Engine
+from .engine import E_SVD_NOCONV, Engine
 from .program import ALIGN, DT, Program, _prod
 
 
@@ -67,6 +67,8 @@ class Compiled:
         rc = eng.run(self.words, soft_errors=soft_errors)
         raw = eng.download(self.out_block.off, self.out_elems)
         slots = eng.slots()
+        if rc == 0 and slots.shape[1] and np.any(slots[:, -1] > 0):     # engine-reserved status slot (include/kbp.h)
+            rc = E_SVD_NOCONV
         outs = []
         for c in range(nb):
             d = {}

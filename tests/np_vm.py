@@ -104,7 +104,7 @@ class NumpyEngine:
                 ar[R:R + kk * n] = r.ravel()
                 i += 7
             elif op == OP_SVD:
-                A, US, Vh, wk, m, n, keep, nrb, s0, s1 = w[i + 1:i + 11]
+                A, US, Vh, wk, m, n, keep, nrb, s0, s1, warm = w[i + 1:i + 12]
                 u, s, vh = np.linalg.svd(ar[A:A + m * n].reshape(m, n), full_matrices=False)
                 fro = np.linalg.norm(s)
                 if s1 >= 0 and fro > 0:
@@ -116,7 +116,7 @@ class NumpyEngine:
                 ar[US:US + m * keep] = (u[:, :keep] * s[:keep]).ravel()
                 ar[Vh:Vh + keep * n] = vh[:keep].ravel()
                 ar[wk:wk + 1] = np.nan  # scratch is clobbered
-                i += 11
+                i += 12
             elif op == OP_NORMALIZE:
                 buf, n, slot = w[i + 1:i + 4]
                 nr = np.linalg.norm(ar[buf:buf + n])

@@ -129,6 +129,39 @@ def test_svd_truncate(eng, m, n, keep):
             assert np.allclose(sv, s[:keep], rtol=1e-10, atol=1e-12 * s[0])
 
 
+@pytest.mark.parametrize("m,n,keep,decay", [(512, 512, 32, 0.08), (256, 512, 32, 0.1), (512, 256, 32, 0.1), (256, 256, 32, 0.12),
+                                            (162, 162, 18, 0.15), (300, 200, 20, 0.2), (512, 512, 32, 0.03)])
+def test_svd_subspace_path(eng, m, n, keep, decay):
+    """boundary-MPS-like spectra (s_j ~ exp(-decay j), near-degenerate cut): the subspace-iteration path must take
+    them (no fallback) and reproduce the exact rank-`keep` truncation."""
+    batch = []
+    for c in range(2):
+        a = rnd(m, n)
+        u, s, vh = np.linalg.svd(a, full_matrices=False)
+        s = np.exp(-decay * np.arange(len(s))) * (1.0 + 0.3 * rng.random(len(s)))
+        s = np.sort(s)[::-1]
+        if c == 1:
+            s[keep] = s[keep - 1] * 0.99       # 1 % gap at the cut
+        batch.append([(u * s) @ vh * 3.7])
+    before = eng.svd_counters()
+    res, sl = run(eng, lambda p, t: list(p.svd_trunc(t[0], keep, True, 0, 1)), batch)
+    after = eng.svd_counters()
+    if decay >= 0.05:
+        assert after["subspace"] == before["subspace"] + 1 and after["subspace_fallback"] == before["subspace_fallback"], (before, after)
+    for c, ((a,), (us, vh)) in enumerate(zip(batch, res)):
+        u, s, v = np.linalg.svd(a, full_matrices=False)
+        fro = np.linalg.norm(s)
+        ref = (u[:, :keep] * s[:keep]) @ v[:keep]
+        got = (us @ vh) * fro
+        gap = (s[keep - 1] - s[keep]) / s[0]
+        assert np.linalg.norm(got - ref) <= 2e-13 * fro / gap, (m, n, keep, c, np.linalg.norm(got - ref) / fro, gap)
+        assert np.linalg.norm(vh @ vh.conj().T - np.eye(keep)) <= 1e-12
+        terr = np.sqrt(np.sum(s[keep:] ** 2) / np.sum(s ** 2))
+        assert abs(sl[c, 1] - terr) <= 1e-10
+        assert abs(sl[c, 0] - np.log(fro)) <= 1e-12 * max(1, abs(np.log(fro)))
+        assert sl[c, -1] == 0
+
+
 def test_normalize_embed_eye(eng):
     a, b = rnd(3, 4, 5), rnd(2, 4, 6)
 

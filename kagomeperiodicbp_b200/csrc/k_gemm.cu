@@ -24,6 +24,7 @@ struct GemmArgs {
   long long C, A, B;
   int m, n, k, opA, opB;
   int ksplit;                     // partial results: C + s * m * n, s < ksplit
+  int rows_on_x;                  // grid.x (2^31 limit) carries the row tiles instead of the column tiles
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
   cplx* Cb = base + (long long)chain * chain_stride + g.C + (long long)split * g.m * g.n;
   const cplx* Ab = base + (long long)chain * chain_stride + g.A;
   const cplx* Bb = base + (long long)chain * chain_stride + g.B;
-  const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+  const int row0 = (g.rows_on_x ? blockIdx.x : blockIdx.y) * BM, col0 = (g.rows_on_x ? blockIdx.y : blockIdx.x) * BN;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int wm = w % WMS, wn = w / WMS;
   const int gq = lane >> 2, q = lane & 3;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
 }
 
 template <int BM, int BN, int STAGES>
-static void launch_gemm(const Arena& a, const GemmArgs& g) {
+static void launch_gemm(const Arena& a, GemmArgs g) {
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
   constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
@@ -165,14 +166,16 @@ static void launch_gemm(const Arena& a, const GemmArgs& g) {
     cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  dim3 grid((unsigned)((g.n + BN - 1) / BN), (unsigned)((g.m + BM - 1) / BM), (unsigned)(a.nb * g.ksplit));
+  const unsigned tn = (unsigned)((g.n + BN - 1) / BN), tm = (unsigned)((g.m + BM - 1) / BM);
+  g.rows_on_x = tm > tn;
+  dim3 grid(g.rows_on_x ? tm : tn, g.rows_on_x ? tn : tm, (unsigned)(a.nb * g.ksplit));
   zgemm_dmma_kernel<BM, BN, STAGES><<<grid, 256, smem, a.stream>>>(a.base, a.chain_stride, g);
   ++*a.launches;
 }
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
   if (m == 0 || n == 0) return;
-  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit};
+  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0};
   const int64_t ctas64 = ((n + 63) / 64) * ((m + 63) / 64) * a.nb * g.ksplit;
   if (ctas64 >= 96) launch_gemm<64, 64, 3>(a, g);
   else launch_gemm<32, 32, 4>(a, g);

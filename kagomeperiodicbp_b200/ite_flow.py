@@ -1,0 +1,145 @@
+"""The ITE step on the device: one loop body of the reference's ``ite_per_mode``
+(src/algo/imaginary_time_evolution/main.py:566-590) --
+
+    robust_belief_propagation (warm messages)              -> belief_propagation.py (six device chains per iteration)
+    reduce_tn(full_tn, ModeTN) / reduce_tn(mode_tn, EdgeTN) -> two device ToCore chains + edge_env.edge_environment
+    ite_update_unit_cell (_tn_update.py:165-205)            -> ite.rho_ij / ite.apply_2local_gate on the device backend
+
+and the energy measurement ``measure_energies_and_observables_together`` (src/algo/measurements.py:163-243: six edge RDMs of
+one mode, energy per site = sum / 3).  Host code orchestrates and moves data; all tensor algebra runs through libkbp.so.
+The core is always reduced with bottom-up direction U (the reference draws it at random from {U, DL, DR},
+kagome_to_core.py:178-179; SURVEY 8d fixes U for reproducible runs).
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import belief_propagation as bp
+from . import edge_env, ite
+from .bubblecon import bubblecon as device_bubblecon
+from .containers import BPConfig, UnitCell
+from .lattice import BLOCK_SIDES_CCW
+from .linalg import DeviceBackend
+from .runtime import get_engine
+
+_backend = None
+
+
+def backend() -> DeviceBackend:
+    global _backend
+    if _backend is None:
+        _backend = DeviceBackend("ite")
+    return _backend
+
+
+def _device_bubblecon_fn(T_list, edges, angles, bubble_angle, order, chi, kets):
+    mp = device_bubblecon([np.ascontiguousarray(t, dtype=np.complex128) for t in T_list], edges, angles, bubble_angle, order,
+                          D_trunc=chi, ket_tensors=kets, engine_key="ite-bubblecon")
+    return mp.A
+
+
+def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device: int = 0):
+    """the 12 ring tensors of the CoreTN (kagome_to_core.py:322-364): two truncated ToCore chains (directions U and D) run
+    concurrently on two streams, then the overlap zip on the device backend."""
+    d, D = unit_cell.A.shape[0], unit_cell.A.shape[1]
+    shapes = bp._msg_shapes(messages)
+    futs = []
+    for side in ("U", "D"):
+        comp = bp.compile_side_program(N, d, D, side, chi, shapes, None, depth="ToCore", epilogue=False)
+        batch = [bp._side_inputs(unit_cell, messages, comp)]
+        futs.append(bp._pool.submit(bp._run_side, side, comp, batch, device))
+    res = {}
+    for f in futs:
+        side, outs, slots, rc = f.result()
+        if slots[0, bp.SLOT_NONFINITE] > 0:
+            raise bp.BubbleConError(f"non-finite values in the ToCore contraction towards {side}")
+        o = outs[0]
+        res[side] = [o[f"out{k}"] for k in range(len(o))]
+    return edge_env.core_env_tensors(backend(), N, res["U"], res["D"])
+
+
+def edge_tn(unit_cell: UnitCell, env12, N: int, mode: str, edge: str, chi: int):
+    """(Ti, Tj, mps_env, info) of the EdgeTN in canonical order (reduce_core_to_mode + reduce_mode_to_edge)."""
+    return edge_env.edge_environment(backend(), N, unit_cell.tensors(), env12, mode, edge, chi, _device_bubblecon_fn)
+
+
+@dataclass
+class MeasurementsOnUnitCell:
+    """(src/containers/results.py:8-20)"""
+    energies: dict
+    rdms: dict = field(default_factory=dict)
+
+    @property
+    def mean_energy(self) -> float:
+        return sum(self.energies.values()) / 3
+
+
+def measure_energies(unit_cell: UnitCell, messages: dict, N: int, chi: int, h=None, mode: str = "A", env12=None) -> MeasurementsOnUnitCell:
+    """(src/algo/measurements.py:163-243, energies part)"""
+    h = ite.heisenberg_afm() if h is None else np.asarray(h)
+    if env12 is None:
+        env12 = reduce_to_core(unit_cell, messages, N, chi)
+    B = backend()
+    energies, rdms = {}, {}
+    for e in edge_env.EDGES:
+        ti, tj, env, _ = edge_tn(unit_cell, env12, N, mode, e, chi)
+        rho = ite.rho_ij(B, ti, tj, env)
+        rdms[e] = rho
+        energies[f"({e[0]}, {e[1]})"] = float(np.real(np.dot(rho.flatten(), h.flatten())))
+    return MeasurementsOnUnitCell(energies, rdms)
+
+
+@dataclass
+class ITEStepStats:
+    bp_iterations: int = 0
+    bp_error: float = 0.0
+    als_iterations: int = 0
+    truncation_distance: float = 0.0
+    t_bp: float = 0.0
+    t_reduce: float = 0.0
+    t_update: float = 0.0
+
+
+def ite_edge_update(unit_cell: UnitCell, messages: dict | None, N: int, mode: str, edge: str, delta_t: float, bp_config: BPConfig,
+                    chi: int, h=None, normalize: bool = True):
+    """one loop body of ite_per_mode with bp_every_edge=True: -> (unit_cell, messages, energy_after, ITEStepStats)."""
+    st = ITEStepStats()
+    h = ite.heisenberg_afm() if h is None else np.asarray(h)
+    g = ite.g_from_exp_h(h, delta_t)
+    B = backend()
+    t0 = time.perf_counter()
+    tn = bp.KagomeTNRepeatedUnitCell(unit_cell, N)
+    messages, bp_stats = bp.robust_belief_propagation(tn, messages, bp_config)
+    st.bp_iterations, st.bp_error = bp_stats.iterations, bp_stats.final_error
+    t1 = time.perf_counter()
+    env12 = reduce_to_core(unit_cell, messages, N, chi)
+    ti, tj, env, info = edge_tn(unit_cell, env12, N, mode, edge, chi)
+    t2 = time.perf_counter()
+    ite.rho_ij(B, ti, tj, env)                                           # _measures_on_edge before the update (_tn_update.py:181)
+    d_virtual = ti.shape[1]
+    ti_new, tj_new, _ = ite.apply_2local_gate(B, g, d_virtual, ti, tj, env)
+    last = getattr(ite.ALS_optimization, "last", None)
+    if last:
+        st.als_iterations, st.truncation_distance = last["iterations"], last["distance"]
+    rho = ite.rho_ij(B, ti_new, tj_new, env)
+    energy = float(np.real(np.dot(rho.flatten(), h.flatten())))
+    if normalize:
+        ti_new = B.scale(ti_new, 1.0 / B.norm(ti_new))
+        tj_new = B.scale(tj_new, 1.0 / B.norm(tj_new))
+    new_cell = edge_env.write_back(unit_cell.tensors(), info, ti_new, tj_new)
+    t3 = time.perf_counter()
+    st.t_bp, st.t_reduce, st.t_update = t1 - t0, t2 - t1, t3 - t2
+    return UnitCell(*new_cell), messages, energy, st
+
+
+def ite_per_mode(unit_cell: UnitCell, messages: dict | None, N: int, mode: str, edge_order, bp_config: BPConfig, chi: int, h=None):
+    """(main.py:540-594)  edge_order: iterable of (edge, delta_t)  -> (unit_cell, messages, edge_energies, [stats])"""
+    energies, stats = {}, []
+    for e, dt in edge_order:
+        unit_cell, messages, energy, st = ite_edge_update(unit_cell, messages, N, mode, e, dt, bp_config, chi, h)
+        energies[f"({e[0]}, {e[1]})"] = energy
+        stats.append(st)
+    return unit_cell, messages, energies, stats

@@ -15,6 +15,8 @@ seeded unit cells (independent states: no data-path collective, weak scaling); r
             SVD ops in an instrumented repetition of the same step; peak = cuBLAS DGEMM measured here
   cpu_baseline  the numpy oracle (port of the reference path, exact-SVD branch) on this box's host cores,
             bounded sample (one chain or a prefix of it)
+  ite       second headline metric (BASELINE.json: "ms per ITE step"): one loop body of ite_per_mode = warm BP to
+            tolerance + two ToCore chains + core->mode->edge reduction + RDM + gate/ALS + energy, wall clock on rank 0
 `--impl reference` times that CPU port as the reference arm (the reference is pure Python + numpy; it cannot
 travel to the GPU box, the oracle is its pinned restatement).
 """
@@ -48,6 +50,10 @@ def parse():
     ap.add_argument("--N", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1, help="unit cells per GPU batched into every launch")
     ap.add_argument("--damping", type=float, default=0.1)
+    ap.add_argument("--shard", default="cells", choices=("cells", "sides"),
+                    help="N > 1: independent unit cells per rank (weak scaling, no collective) or the six sides of ONE cell "
+                         "sharded over the ranks with one all-gather of the new messages per iteration (strong scaling)")
+    ap.add_argument("--ite-steps", type=int, default=3, help="ITE steps (loop bodies of ite_per_mode) timed on rank 0 at N=1; 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
@@ -122,6 +128,49 @@ def cpu_sample(a, cell, messages, budget_s):
             "sample": f"oracle (numpy port of the reference path, exact-SVD branch) on {k}/{len(order)} swallows of one ToMessage chain "
                       f"(side D) of the same workload, {t:.1f} s measured" + ("" if k == len(order) else f", extrapolated to {t_full:.1f} s per message"),
             "seconds_per_message": t_full}
+
+
+def ite_metric(a, cell, messages, cfg, cpu_bp):
+    """ms per ITE step: loop bodies of ite_per_mode (BASELINE.json's second metric) on the device, wall clock, after one
+    untimed pass over the same edges (program compilation + arena allocation), messages warm as in a running ITE."""
+    from kagomeperiodicbp_b200 import edge_env, ite_flow
+    chi = 2 * a.D * a.D + 10
+    edges = [edge_env.EDGES[k % 6] for k in range(a.ite_steps)]
+    uc, msgs = cell, messages
+    for e in edges:                                   # warm-up pass
+        uc, msgs, _, _ = ite_flow.ite_edge_update(uc, msgs, a.N, "A", e, 1e-2, cfg, chi)
+    ts, parts, its, energies = [], [0.0, 0.0, 0.0], [], []
+    for e in edges:
+        t0 = time.perf_counter()
+        uc, msgs, energy, st = ite_flow.ite_edge_update(uc, msgs, a.N, "A", e, 1e-2, cfg, chi)
+        ts.append(time.perf_counter() - t0)
+        parts = [parts[0] + st.t_bp, parts[1] + st.t_reduce, parts[2] + st.t_update]
+        its.append(st.bp_iterations)
+        energies.append(energy)
+    out = {"metric": "ms_per_ite_step", "value": 1e3 * float(np.mean(ts)), "unit": "ms", "higher_is_better": False, "steps": len(ts),
+           "edges": edges, "mode": "A", "delta_t": 1e-2, "chi": chi, "bp_iterations_per_step": its,
+           "breakdown_ms": {"bp": 1e3 * parts[0] / len(ts), "reduce_to_edge": 1e3 * parts[1] / len(ts), "rdm_gate_als": 1e3 * parts[2] / len(ts)},
+           "edge_energies_after": energies, "device_linalg_calls": ite_flow.backend().calls}
+    if cpu_bp is not None:
+        # CPU side of the same step, composed from timed parts: BP iterations and the two ToCore chains at the oracle's
+        # seconds per chain (measured above), core -> edge reduction + RDM + gate/ALS timed here with numpy/LAPACK
+        from oracle import ite_np
+        from oracle.bubblecon_np import bubblecon as obub
+        from kagomeperiodicbp_b200 import ite
+        env12 = ite_flow.reduce_to_core(uc, msgs, a.N, chi)             # inputs for the host-timed part
+        t0 = time.perf_counter()
+        fn = lambda T, E, A, ang, order, c, kets: obub(T, E, A, ang, order, D_trunc=c, ket_tensors=kets).A
+        ti, tj, env, _ = edge_env.edge_environment(ite_np.NP, a.N, uc.tensors(), env12, "A", edges[0], chi, fn)
+        ite_np.rho_ij(ti, tj, env)
+        tin, tjn, _ = ite_np.apply_2local_gate(ite.g_from_exp_h(ite.heisenberg_afm(), 1e-2), a.D, ti, tj, env)
+        ite_np.rho_ij(tin, tjn, env)
+        t_edge = time.perf_counter() - t0
+        spm = cpu_bp["seconds_per_message"]
+        cpu_ms = 1e3 * ((6 * float(np.mean(its)) + 2) * spm + t_edge)
+        out["cpu_baseline"] = {"value": cpu_ms, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"composed: ({float(np.mean(its)):.1f} BP iterations x 6 + 2 ToCore) chains at {spm:.2f} s per chain (oracle, "
+                                         f"measured above) + core->edge reduction, RDM, gate/ALS for edge {edges[0]} timed with numpy ({t_edge:.2f} s)"}
+    return out
 
 
 def run_reference_arm(a, rank):
@@ -239,26 +288,50 @@ def main():
         bp.bp_step_batch(N, cells, msgs_list, cfg, device=dev)
         torch.cuda.synchronize()
         t_e2e += time.perf_counter() - t0
+    # ---- sides sharded over the ranks: one all-gather of the new messages per iteration (config C3)
+    ms_sharded, gather_bytes = None, 0
+    if a.shard == "sides" and world > 1:
+        from kagomeperiodicbp_b200 import parallel
+        tdev = torch.device("cuda", local)
+        for _ in range(a.warmup):
+            parallel.bp_step_sharded(N, cells[:1], msgs_list[:1], cfg, rank, world, dev, torch_device=tdev)
+        tot = 0.0
+        for i in range(a.steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            _, gather_bytes = parallel.bp_step_sharded(N, cells[:1], msgs_list[:1], cfg, rank, world, dev, torch_device=tdev)
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t0
+        ms_sharded = 1e3 * tot / a.steps
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     ms_step = ms_total / a.steps
     ms_e2e = 1e3 * t_e2e / a.steps
     if world > 1:
-        t = torch.tensor([ms_step, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms_step, ms_e2e, ms_sharded or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, ms_e2e = float(t[0]), float(t[1])
+        ms_sharded = float(t[2]) if ms_sharded is not None else None
         tl = torch.tensor([n_launch], device="cuda", dtype=torch.int64)
         dist.all_reduce(tl)
         n_launch = int(tl[0])
     units = 6 * B * world
     value = units / (ms_step * 1e-3)
     e2e_value = units / (ms_e2e * 1e-3)
+    scaling, sharding = "weak", "independent unit cells per rank, no data-path collective"
+    if ms_sharded is not None:
+        # strong scaling: the six messages of ONE cell; the all-gather needs host-visible results, so value == e2e here
+        units, scaling = 6, "strong"
+        value = e2e_value = units / (ms_sharded * 1e-3)
+        ms_step = ms_e2e = ms_sharded
+        sharding = f"six block sides of one unit cell round-robin over {world} ranks, one NCCL all-gather of {gather_bytes} B per iteration"
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "c128",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "unit_cells_per_gpu": B, "sharding": "independent unit cells per rank, no data-path collective",
+            "config": {"workload": workload_name(a), "unit_cells_per_gpu": B, "sharding": sharding,
                        "l2": "512 MiB buffer rewritten between timed iterations (L2 flush)",
                        "swallows_per_message": len(bp.contraction_order.kagome_order(N, "D", "ToMessage")) - 1},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
@@ -297,16 +370,19 @@ def main():
         share = svd_ms / max(1e-9, float(ms.sum()))
         achieved = svd_flops / (ms_step * 1e-3 * share) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": "svd_round_kernel (block-Jacobi truncated SVD, FP64 DMMA)",
+                            "kernel": "truncated-SVD family (zgemm_dmma_kernel + chol_inv_kernel + svd_small_kernel subspace iteration; svd_round_kernel fallback)",
                             "peak_source": "cuBLAS DGEMM 4096^3 FP64 measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
                             "algorithmic_flops_per_step": svd_flops, "svd_share_of_op_time": share,
                             "all_ops_algorithmic_flops_per_step": total_flops,
                             "all_ops_achieved_tflops": total_flops / (ms_step * 1e-3) / 1e12,
                             "op_time_ms": {k: float(ms[i]) for k, i in (("permute", 1), ("gemm", 2), ("qr", 3), ("svd", 4), ("normalize", 5), ("embed", 6), ("zero", 7), ("eye", 10))},
                             "op_counts": {k: int(cnt[i]) for k, i in (("permute", 1), ("gemm", 2), ("qr", 3), ("svd", 4))},
-                            "jacobi_sweeps_total": sum(engs[s].svd_sweeps() for s in BLOCK_SIDES_CCW)}
+                            "jacobi_sweeps_total": sum(engs[s].svd_sweeps() for s in BLOCK_SIDES_CCW),
+                            "svd_paths": {k: sum(engs[s].svd_counters()[k] for s in BLOCK_SIDES_CCW) for k in engs[BLOCK_SIDES_CCW[0]].svd_counters()}}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(a, cells[0], msgs_list[0], a.cpu_budget_s)
+        if world == 1 and a.ite_steps > 0:
+            line["ite"] = ite_metric(a, cells[0], msgs_list[0], cfg, line.get("cpu_baseline"))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

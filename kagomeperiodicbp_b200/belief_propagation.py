@@ -231,16 +231,16 @@ def _run_side(side: str, comp: Compiled, batch_inputs: list, device: int):
     return side, outs, slots, rc
 
 
-def bp_step_batch(N: int, cells: list, messages_list: list, config: BPConfig, device: int = 0):
-    """one BP iteration for a batch of independent unit cells that share all shapes.  Returns per cell
-    (out_messages, next_messages, error, trunc_error)."""
+def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device: int = 0, sides=None) -> dict:
+    """run the chain programs of ``sides`` (default: all six) concurrently, one CUDA stream each.
+    -> {side: (outs per cell, slots[nb, n_slots], rc)}"""
     d, D = cells[0].A.shape[0], cells[0].A.shape[1]
     shapes = _msg_shapes(messages_list[0])
     for m in messages_list[1:]:
         assert _msg_shapes(m) == shapes, "batched cells must share message shapes"
     damping = config.damping if config.damping else None
     futs = []
-    for side in BLOCK_SIDES_CCW:
+    for side in (BLOCK_SIDES_CCW if sides is None else sides):
         comp = compile_side_program(N, d, D, side, config.trunc_dim, shapes, damping)
         batch = [_side_inputs(c, m, comp) for c, m in zip(cells, messages_list)]
         futs.append(_pool.submit(_run_side, side, comp, batch, device))
@@ -248,9 +248,15 @@ def bp_step_batch(N: int, cells: list, messages_list: list, config: BPConfig, de
     for f in futs:
         side, outs, slots, rc = f.result()
         res[side] = (outs, slots, rc)
-    L = 2 * N - 1
+    return res
+
+
+def assemble_step(res: dict, n_cells: int, config: BPConfig):
+    """per cell (out_messages, next_messages, error, trunc_error) from the six sides' raw results: relabel to the
+    opposite side (periodic block, reference :155), error = mean of 1 - |<prev|out>| (:44-56)."""
+    damping = config.damping if config.damping else None
     results = []
-    for ci in range(len(cells)):
+    for ci in range(n_cells):
         out_msgs, next_msgs, dists, trunc = {}, {}, [], 0.0
         for side in BLOCK_SIDES_CCW:
             outs, slots, rc = res[side]
@@ -275,6 +281,12 @@ def bp_step_batch(N: int, cells: list, messages_list: list, config: BPConfig, de
             err = float(np.sqrt(sum(dists)) / len(dists))
         results.append((out_msgs, next_msgs if damping else out_msgs, float(err), trunc))
     return results
+
+
+def bp_step_batch(N: int, cells: list, messages_list: list, config: BPConfig, device: int = 0):
+    """one BP iteration for a batch of independent unit cells that share all shapes.  Returns per cell
+    (out_messages, next_messages, error, trunc_error)."""
+    return assemble_step(run_sides(N, cells, messages_list, config, device), len(cells), config)
 
 
 def _belief_propagation_step(tn: KagomeTNRepeatedUnitCell, prev_messages: dict, prev_error, config: BPConfig, prog_bar_obj=None):

@@ -51,8 +51,56 @@ bool svd_small_fits(int64_t m, int64_t n) {
   return m <= n && m <= 128 && svd_small_smem(m, n) <= SMALL_SMEM_MAX;
 }
 
-__global__ void __launch_bounds__(1024) svd_small_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
-                                                         int n_slots, SmallArgs g) {
+// rotate one row pair with both rows held in registers between the Gram sums and the update (CPL columns per lane)
+template <int CPL>
+__device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int G, int gl, unsigned gmask,
+                                                   double floor2, double& my_off) {
+  cplx u[CPL], v[CPL];
+  double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = gl + k * G;
+    u[k] = c < q ? xi[c] : cmake(0.0, 0.0);
+    v[k] = c < q ? xj[c] : cmake(0.0, 0.0);
+    a = fma(u[k].x, u[k].x, fma(u[k].y, u[k].y, a));
+    b = fma(v[k].x, v[k].x, fma(v[k].y, v[k].y, b));
+    cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));
+    ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
+  }
+  for (int o = G >> 1; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(gmask, a, o);
+    b += __shfl_xor_sync(gmask, b, o);
+    cr += __shfl_xor_sync(gmask, cr, o);
+    ci += __shfl_xor_sync(gmask, ci, o);
+  }
+  const double r2 = fma(cr, cr, ci * ci);
+  if (!(a > floor2 && b > floor2 && r2 > 0.0)) return;
+  const double off = sqrt(r2 / (a * b));
+  my_off = fmax(my_off, off);
+  if (!(off > SMALL_TOL)) return;
+  const double ab = sqrt(r2), inv = 1.0 / ab;
+  const double er = cr * inv, ei = ci * inv;
+  const double d = a - b;
+  double tt = 2.0 * ab / (fabs(d) + sqrt(fma(d, d, 4.0 * r2)));
+  if (d < 0.0) tt = -tt;
+  const double cs = rsqrt(fma(tt, tt, 1.0)), sn = tt * cs;
+  const bool swap = d < 0.0;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = gl + k * G;
+    if (c < q) {
+      const double vr = er * v[k].x - ei * v[k].y, vi = er * v[k].y + ei * v[k].x;
+      const cplx yi = make_double2(fma(cs, u[k].x, sn * vr), fma(cs, u[k].y, sn * vi));
+      const cplx yj = make_double2(fma(cs, vr, -sn * u[k].x), fma(cs, vi, -sn * u[k].y));
+      xi[c] = swap ? yj : yi;
+      xj[c] = swap ? yi : yj;
+    }
+  }
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
+                                                                        int n_slots, SmallArgs g) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int m = g.m, n = g.n;
   const bool mode_t = m > n;
@@ -101,7 +149,18 @@ __global__ void __launch_bounds__(1024) svd_small_kernel(cplx* __restrict__ base
       if (slot < npairs) {
         int i, j;
         rr_pair_s(pp, step, slot, i, j);
-        if (j < p) {
+        if (CACHED && j < p) {
+          cplx* xi = X + i * q;
+          cplx* xj = X + j * q;
+          switch ((q + G - 1) / G) {
+            case 1: jacobi_pair_cached<1>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            case 2: jacobi_pair_cached<2>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            case 3: jacobi_pair_cached<3>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            case 4: jacobi_pair_cached<4>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            case 5: jacobi_pair_cached<5>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            default: jacobi_pair_cached<6>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+          }
+        } else if (j < p) {
           cplx* xi = X + i * q;
           cplx* xj = X + j * q;
           double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
@@ -229,7 +288,8 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
                int slot_lognorm, int slot_trunc) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
     attr_set = true;
   }
   SmallArgs g;
@@ -243,7 +303,11 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
   threads = (threads + 31) / 32 * 32;
   if (threads < 256) threads = 256;
   if (threads > 1024) threads = 1024;
-  svd_small_kernel<<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
+  const int q = (int)(m < n ? n : m);
+  if (threads <= 768 && (q + G - 1) / G <= 6)
+    svd_small_kernel<true><<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
+  else
+    svd_small_kernel<false><<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
   ++*a.launches;
 }
 

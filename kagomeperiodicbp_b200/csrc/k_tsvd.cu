@@ -2,7 +2,7 @@
 // mps.right_canonical asks for (src/libs/bmpslib.py:733-772) keeps chi = 2 D^2 of chi D^2 singular triplets,
 // so the full factorisation numpy computes there is ~10x more work than the answer needs.
 //
-//   Q0 (n x b) pseudo-random, b = 3 keep                              [deterministic hash, no RNG state]
+//   Q0 (n x b) pseudo-random, b = 2.5 keep                             [deterministic hash, no RNG state]
 //   repeat:  W = A Q ;  Y = orth(W) ;  Z = A^H Y ;  Q = orth(Z)        [DMMA ZGEMMs + Cholesky-QR]
 //   Rayleigh-Ritz:  W = A Q = Y R  (Cholesky-QR twice, R = R2 R1, b x b),  R = Ur S Vb^H  by the in-smem
 //   Jacobi kernel (k_svd_small.cu) ->  Vh = Vb_k^H Q^H  (keep x n, orthonormal rows),  US = A Vh^H.
@@ -27,19 +27,19 @@ namespace kbp {
 constexpr int TSVD_BMAX = 112;            // b x b complex must fit one CTA's shared memory (chol + small SVD)
 constexpr double TSVD_RES_TOL = 2e-13;
 constexpr double TSVD_PIVOT_DEAD = 1e-13;  // pivot / diagonal below this: the column is numerically dependent -> dropped
-// Dropped directions carry at most ~3e-7 of a column's norm.  They can only belong to the kept triplets when the
-// spectrum collapses inside the kept part, so a block whose keep-th Ritz value is below this fraction of the first
-// goes to the exact path instead.
-constexpr double TSVD_MIN_RATIO = 3e-6;
+// Dropped directions carry at most ~3e-7 of a column's norm (pivot ratio 1e-13), i.e. singular values below 3e-7 s_1.
+// They can only belong to the kept triplets when the spectrum collapses inside the kept part, so a block whose keep-th
+// Ritz value is below this fraction of the first (pivot ratio 1e-12: 10x above the drop threshold) goes to the exact path.
+constexpr double TSVD_MIN_RATIO = 1e-6;
 
 static inline int64_t rup8(int64_t x) { return (x + 7) / 8 * 8; }
 
 int tsvd_block(int64_t m, int64_t n, int64_t keep) {
-  static const int factor_x10 = getenv("KBP_TSVD_FACTOR_X10") ? atoi(getenv("KBP_TSVD_FACTOR_X10")) : 30;
+  static const int factor_x10 = getenv("KBP_TSVD_FACTOR_X10") ? atoi(getenv("KBP_TSVD_FACTOR_X10")) : 25;
   const int64_t p = m < n ? m : n;
   int64_t b = rup8(keep * factor_x10 / 10);
   if (b > TSVD_BMAX) b = TSVD_BMAX;
-  if (b < keep + 8 || b * 100 > p * 65) return 0;     // not worth it / not applicable
+  if (b < keep + 8 || b * 100 > p * 80) return 0;     // not worth it / not applicable
   return (int)b;
 }
 
@@ -77,8 +77,9 @@ constexpr int CNB = 16;
 __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit,
                                                         long long R_, long long Rinv_, int b, double* __restrict__ stat) {
   extern __shared__ __align__(16) unsigned char ch_raw[];
-  cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x b
-  double* diag0 = reinterpret_cast<double*>(S + (size_t)b * b);    // original diagonal
+  const int ld = b + 1;                                            // odd row stride: the 16 rows of a panel fall into different banks
+  cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x ld
+  double* diag0 = reinterpret_cast<double*>(S + (size_t)b * ld);   // original diagonal
   double* dinv = diag0 + b;                                        // 1 / R_jj (0 for dropped columns)
   __shared__ double sh_min;
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
@@ -87,10 +88,10 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   for (int e = t; e < b * b; e += nt) {
     cplx v = G[e];
     for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, G[(long long)sp * b * b + e]);
-    S[e] = v;
+    S[(e / b) * ld + e % b] = v;
   }
   __syncthreads();
-  for (int i = t; i < b; i += nt) diag0[i] = S[i * b + i].x;
+  for (int i = t; i < b; i += nt) diag0[i] = S[i * ld + i].x;
   if (t == 0) sh_min = 1.0;
   __syncthreads();
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       double mn = 1.0;
       const int li = p0 + (lane >> 1), lc0 = p0 + (lane & 1) * 8;
       for (int j = p0; j < p1; ++j) {
-        const double d = S[j * b + j].x, d0 = diag0[j];
+        const double d = S[j * ld + j].x, d0 = diag0[j];
         const bool live = d0 > 0.0 && d > TSVD_PIVOT_DEAD * d0;      // NaN -> dropped
         const double ip = live ? rsqrt(d) : 0.0;
         if (live) mn = fmin(mn, d / d0);
@@ -111,22 +112,22 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int l = lc0 + u;
-            if (l > j && l < p1) S[j * b + l] = cscale(S[j * b + l], ip);
-            else if (l == j) { S[j * b + j] = cmake(live ? d * ip : 0.0, 0.0); dinv[j] = ip; }
+            if (l > j && l < p1) S[j * ld + l] = cscale(S[j * ld + l], ip);
+            else if (l == j) { S[j * ld + j] = cmake(live ? d * ip : 0.0, 0.0); dinv[j] = ip; }
           }
         }
         __syncwarp();
         if (li > j && li < p1) {
-          const cplx rji = S[j * b + li];
+          const cplx rji = S[j * ld + li];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int l = lc0 + u;
             if (l >= li && l < p1) {
-              const cplx v = ccmul(rji, S[j * b + l]);
-              cplx x = S[li * b + l];
+              const cplx v = ccmul(rji, S[j * ld + l]);
+              cplx x = S[li * ld + l];
               x.x -= v.x; x.y -= v.y;
               if (l == li) x.y = 0.0;
-              S[li * b + l] = x;
+              S[li * ld + l] = x;
             }
           }
         }
@@ -142,12 +143,12 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
         for (int i = p1 - 2; i >= p0; --i) {
           cplx acc = cmake(0.0, 0.0);
           if (act && i < l) {
-            if (half == 0) acc = cscale(S[i * b + l], xll);              // R[i][l] x_ll
-            for (int r = i + 1 + half; r < l; r += 2) acc = cfma(S[i * b + r], S[l * b + r], acc);
+            if (half == 0) acc = cscale(S[i * ld + l], xll);              // R[i][l] x_ll
+            for (int r = i + 1 + half; r < l; r += 2) acc = cfma(S[i * ld + r], S[l * ld + r], acc);
           }
           acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
           acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-          if (act && i < l && half == 0) S[l * b + i] = cscale(acc, -dinv[i]);
+          if (act && i < l && half == 0) S[l * ld + i] = cscale(acc, -dinv[i]);
           __syncwarp();
         }
       }
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
         outv[u] = cmake(0.0, 0.0);
         if (e < nel) {
           const int r = p0 + e / rem, l = p1 + e % rem;
-          cplx acc = cscale(S[r * b + l], dinv[r]);
-          for (int rp = p0; rp < r; ++rp) acc = cadd(acc, ccmul(S[r * b + rp], S[rp * b + l]));
+          cplx acc = cscale(S[r * ld + l], dinv[r]);
+          for (int rp = p0; rp < r; ++rp) acc = cadd(acc, ccmul(S[r * ld + rp], S[rp * ld + l]));
           outv[u] = acc;
         }
       }
@@ -173,20 +174,20 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int e = t + u * 1024;
-        if (e < nel) S[(p0 + e / rem) * b + p1 + e % rem] = outv[u];
+        if (e < nel) S[(p0 + e / rem) * ld + p1 + e % rem] = outv[u];
       }
       __syncthreads();
       // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
       for (int e = t; e < rem * rem; e += nt) {
         const int i = p1 + e / rem, l = p1 + e % rem;
         if (l >= i) {
-          cplx x = S[i * b + l];
+          cplx x = S[i * ld + l];
           for (int r = p0; r < p1; ++r) {
-            const cplx v = ccmul(S[r * b + i], S[r * b + l]);
+            const cplx v = ccmul(S[r * ld + i], S[r * ld + l]);
             x.x -= v.x; x.y -= v.y;
           }
           if (l == i) x.y = 0.0;
-          S[i * b + l] = x;
+          S[i * ld + l] = x;
         }
       }
       __syncthreads();
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   }
   if (R_ >= 0) {
     cplx* R = cb + R_;
-    for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[e] : cmake(0.0, 0.0);
+    for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[(e / b) * ld + e % b] : cmake(0.0, 0.0);
   }
   __syncthreads();
   // ---- off-diagonal blocks of the inverse, level d = block column - block row:
@@ -210,8 +211,8 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       if (e < nel) {
         const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
         if (l < b) {
-          cplx acc = cscale(S[ip * b + l], dinv[l]);               // j == l
-          for (int j = (pb + 1) * CNB; j < l; ++j) acc = cfma(S[ip * b + j], S[l * b + j], acc);
+          cplx acc = cscale(S[ip * ld + l], dinv[l]);               // j == l
+          for (int j = (pb + 1) * CNB; j < l; ++j) acc = cfma(S[ip * ld + j], S[l * ld + j], acc);
           tv[u] = acc;
         }
       }
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       const int e = t + u * 1024;
       if (e < nel) {
         const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) S[l * b + ip] = tv[u];                           // T, parked where X_pq will go
+        if (l < b) S[l * ld + ip] = tv[u];                           // T, parked where X_pq will go
       }
     }
     __syncthreads();
@@ -233,8 +234,8 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       if (e < nel) {
         const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
         if (l < b) {
-          cplx acc = cscale(S[l * b + i], dinv[i]);                 // i' == i
-          for (int ip = i + 1; ip < (pb + 1) * CNB; ++ip) acc = cfma(S[ip * b + i], S[l * b + ip], acc);
+          cplx acc = cscale(S[l * ld + i], dinv[i]);                 // i' == i
+          for (int ip = i + 1; ip < (pb + 1) * CNB; ++ip) acc = cfma(S[ip * ld + i], S[l * ld + ip], acc);
           tv[u] = cmake(-acc.x, -acc.y);
         }
       }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       const int e = t + u * 1024;
       if (e < nel) {
         const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) S[l * b + i] = tv[u];
+        if (l < b) S[l * ld + i] = tv[u];
       }
     }
     __syncthreads();
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   cplx* Rinv = cb + Rinv_;
   for (int e = t; e < b * b; e += nt) {
     const int i = e / b, l = e % b;
-    Rinv[e] = i < l ? S[l * b + i] : (i == l ? cmake(dinv[i], 0.0) : cmake(0.0, 0.0));
+    Rinv[e] = i < l ? S[l * ld + i] : (i == l ? cmake(dinv[i], 0.0) : cmake(0.0, 0.0));
   }
   if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], sh_min);
 }
@@ -418,7 +419,7 @@ constexpr int GRAM_SPLIT = 4;
 static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Rinv, int64_t R_out, int64_t rows, int b, double* stat) {
   const int split = rows >= 256 ? GRAM_SPLIT : 1;
   gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
-  const size_t smem = sizeof(double2) * (size_t)b * b + 2 * sizeof(double) * (size_t)b + 32;
+  const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 2 * sizeof(double) * (size_t)b + 32;
   chol_inv_kernel<<<a.nb, 1024, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Rinv, b, stat);
   ++*a.launches;
   if (T >= 0) gemm(a, T, Y, Rinv, rows, b, b, OP_N, OP_N);      // T < 0: only R is wanted
@@ -442,7 +443,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     attr_set = true;
   }
   static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 2;
+  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 5;
   static const int it_warm = getenv("KBP_TSVD_ITWARM") ? atoi(getenv("KBP_TSVD_ITWARM")) : 2;
   static const int it_step = getenv("KBP_TSVD_ITSTEP") ? atoi(getenv("KBP_TSVD_ITSTEP")) : 3;
   static const int it_max = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 24;

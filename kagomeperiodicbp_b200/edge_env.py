@@ -123,7 +123,7 @@ def core_network(B, N: int, cell, env12):
         kets[k] = (np.asarray(cell[flavor[tb[k]["name"]]]), list(tb[k]["edges"]))
     envs = {}
     for i in range(12):
-        envs[i] = Node(np.asarray(env12[i]), list(tb[9 + i]["edges"]))
+        envs[i] = Node(env12[i], list(tb[9 + i]["edges"]))
     return kets, envs
 
 
@@ -167,18 +167,32 @@ class Core:
         return members
 
     def composite(self, members) -> Node:
-        """contract the member nodes (greedy: always a node that shares a leg with what has been accumulated)."""
-        todo = list(members)
-        acc = self.node(todo.pop(0))
-        while todo:
-            for q, key in enumerate(todo):
-                if set(self.legs_of(key)) & set(acc.legs):
-                    acc = contract(self.B, acc, self.node(key))
-                    todo.pop(q)
-                    break
-            else:
+        """contract the member nodes exactly.  Greedy pairwise order: always the connected pair whose product is
+        smallest (the order is free -- exact contraction -- and a bad one creates intermediates with many open D^2 legs)."""
+        nodes = [self.node(k) for k in members]
+        while len(nodes) > 1:
+            best = None
+            for x in range(len(nodes)):
+                for y in range(x + 1, len(nodes)):
+                    a, b = nodes[x], nodes[y]
+                    common = [e for e in a.legs if e in b.legs]
+                    if not common:
+                        continue
+                    size = 1
+                    for e, dsz in zip(a.legs, a.t.shape):
+                        if e not in common:
+                            size *= dsz
+                    for e, dsz in zip(b.legs, b.t.shape):
+                        if e not in common:
+                            size *= dsz
+                    if best is None or size < best[0]:
+                        best = (size, x, y)
+            if best is None:
                 raise AssertionError(("disconnected composite", members))
-        return acc
+            _, x, y = best
+            c = contract(self.B, nodes[x], nodes[y])
+            nodes = [n for k, n in enumerate(nodes) if k not in (x, y)] + [c]
+        return nodes[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,7 +277,7 @@ def edge_environment(B, N: int, cell, env12, mode: str, edge: str, chi: int, bub
     for n in ring:
         a, d2, b = n.t.shape
         assert d2 == D * D
-        env.append(np.ascontiguousarray(np.reshape(n.t, (a, D, D, b))))
+        env.append(B.reshape(n.t, (a, D, D, b)))
     # consistency of the ring with the sites' canonical legs
     ti_legs = [core.kets[ki][1][p] for p in pi]
     tj_legs = [core.kets[kj][1][p] for p in pj]
@@ -281,5 +295,5 @@ def write_back(cell, info, Ti_new, Tj_new):
     cell = list(cell)
     for f, perm, t in ((info["flavors"][0], info["perm_i"], Ti_new), (info["flavors"][1], info["perm_j"], Tj_new)):
         inv = np.argsort(perm)
-        cell[flavor[f]] = np.ascontiguousarray(np.transpose(t, [0] + [1 + int(p) for p in inv]))
+        cell[flavor[f]] = np.ascontiguousarray(np.transpose(np.asarray(t), [0] + [1 + int(p) for p in inv]))
     return cell

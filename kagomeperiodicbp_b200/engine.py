@@ -90,8 +90,8 @@ def svd_warm_elems(m: int, n: int, keep: int) -> int:
     p = min(m, n)
     if m <= n and m <= 128 and p * max(m, n) * 16 + p * 12 + 64 <= 225 * 1024:
         return 0                                  # in-shared-memory Jacobi
-    b = min(112, (3 * keep + 7) // 8 * 8)
-    if b < keep + 8 or b * 100 > p * 65:
+    b = min(112, (keep * 25 // 10 + 7) // 8 * 8)
+    if b < keep + 8 or b * 100 > p * 80:
         return 0
     return n * 112
 

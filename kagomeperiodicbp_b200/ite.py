@@ -59,7 +59,7 @@ def rho_ij(B, Ti, Tj, mps_env):
     rho = B.tensordot(Ai, Aj, ([2, 3, 4, 5], [2, 3, 5, 4]))
     d = rho.shape[0]
     tr = np.trace(np.trace(np.asarray(rho), axis1=0, axis2=1))       # scalar
-    return B.scale(rho, 1.0 / tr)
+    return np.asarray(B.scale(rho, 1.0 / tr))
 
 
 def _n_half(B, T_rest, envs, n_legs):
@@ -247,7 +247,7 @@ def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env):
         g_i, g_j = g[:, :, mi[2], mi[3]], g[mi[0], mi[1], :, :]
         rescale = g[mi] / (g_i[mi[0], mi[1]] * g_j[mi[2], mi[2]])
         fi = np.sqrt(abs(rescale))
-        return (B.tensordot(fi * g_i, Ti, ([1], [0])), B.tensordot((rescale / fi) * g_j, Tj, ([1], [0])), None)
+        return (np.asarray(B.tensordot(fi * g_i, Ti, ([1], [0]))), np.asarray(B.tensordot((rescale / fi) * g_j, Tj, ([1], [0]))), None)
     X, ai, aj, Ti_rest, Tj_rest, w = reduced_env(B, Ti, Tj, mps_env)
     d, Di_red, Dj_red = ai.shape[0], ai.shape[2], aj.shape[2]
     ex = B.tensordot(ai, aj, ([1], [1]))                               # [d, Di, d, Dj]
@@ -263,8 +263,8 @@ def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env):
     new_ai, new_aj = ALS_optimization(B, Dmax, exact_ai, exact_aj, X)
     new_Ti = B.tensordot(new_ai, Ti_rest, ([2], [0]))
     new_Tj = B.tensordot(new_aj, Tj_rest, ([2], [0]))
-    new_Ti = B.scale(new_Ti, 1.0 / float(np.max(np.abs(np.asarray(new_Ti)))))
-    new_Tj = B.scale(new_Tj, 1.0 / float(np.max(np.abs(np.asarray(new_Tj)))))
+    new_Ti = np.asarray(B.scale(new_Ti, 1.0 / float(np.max(np.abs(np.asarray(new_Ti))))))
+    new_Tj = np.asarray(B.scale(new_Tj, 1.0 / float(np.max(np.abs(np.asarray(new_Tj))))))
     return new_Ti, new_Tj, w
 
 

@@ -22,21 +22,21 @@ from . import edge_env, ite
 from .bubblecon import bubblecon as device_bubblecon
 from .containers import BPConfig, UnitCell
 from .lattice import BLOCK_SIDES_CCW
-from .linalg import DeviceBackend
+from .linalg import ResidentBackend
 from .runtime import get_engine
 
 _backend = None
 
 
-def backend() -> DeviceBackend:
+def backend() -> ResidentBackend:
     global _backend
     if _backend is None:
-        _backend = DeviceBackend("ite")
+        _backend = ResidentBackend("ite")
     return _backend
 
 
 def _device_bubblecon_fn(T_list, edges, angles, bubble_angle, order, chi, kets):
-    mp = device_bubblecon([np.ascontiguousarray(t, dtype=np.complex128) for t in T_list], edges, angles, bubble_angle, order,
+    mp = device_bubblecon([np.ascontiguousarray(np.asarray(t), dtype=np.complex128) for t in T_list], edges, angles, bubble_angle, order,
                           D_trunc=chi, ket_tensors=kets, engine_key="ite-bubblecon")
     return mp.A
 
@@ -88,7 +88,7 @@ def measure_energies(unit_cell: UnitCell, messages: dict, N: int, chi: int, h=No
         ti, tj, env, _ = edge_tn(unit_cell, env12, N, mode, e, chi)
         rho = ite.rho_ij(B, ti, tj, env)
         rdms[e] = rho
-        energies[f"({e[0]}, {e[1]})"] = float(np.real(np.dot(rho.flatten(), h.flatten())))
+        energies[f"({e[0]}, {e[1]})"] = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
     return MeasurementsOnUnitCell(energies, rdms)
 
 
@@ -125,7 +125,7 @@ def ite_edge_update(unit_cell: UnitCell, messages: dict | None, N: int, mode: st
     if last:
         st.als_iterations, st.truncation_distance = last["iterations"], last["distance"]
     rho = ite.rho_ij(B, ti_new, tj_new, env)
-    energy = float(np.real(np.dot(rho.flatten(), h.flatten())))
+    energy = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
     if normalize:
         ti_new = B.scale(ti_new, 1.0 / B.norm(ti_new))
         tj_new = B.scale(tj_new, 1.0 / B.norm(tj_new))

@@ -136,3 +136,175 @@ class DeviceBackend:
         w = (s - _EIG_SHIFT) * nrm
         order = np.argsort(w, kind="stable")
         return w[order], np.conj(vh[order]).T
+
+
+# ------------------------------------------------------------------------------------------------
+# resident executor: the same operations, but tensors stay in HBM between calls
+# ------------------------------------------------------------------------------------------------
+class RArr:
+    """handle of a tensor that lives in the resident backend's arena.  Converting it to numpy (np.asarray, indexing)
+    downloads it; the ITE algebra only does that for small tensors and for scalar decisions."""
+    __slots__ = ("B", "dt")
+
+    def __init__(self, B, dt):
+        self.B, self.dt = B, dt
+
+    shape = property(lambda self: self.dt.shape)
+    ndim = property(lambda self: self.dt.ndim)
+    size = property(lambda self: self.dt.size)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.B.to_host(self)
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self.B.to_host(self)[idx]
+
+    def copy(self):
+        return self                      # tensors are never modified in place by the backend
+
+
+class ResidentBackend:
+    """eager device execution with a persistent arena: every call appends a few ops to one growing tensor program and
+    launches them asynchronously on the context's stream; buffers are recycled by the program's first-fit allocator when
+    their Python handles die (all work is stream-ordered, so reuse is safe).  Host <-> device traffic is limited to the
+    inputs (unit-cell tensors, ring tensors of the ToCore chains), small matrices built on the host (diag(sqrt(S)), ...)
+    and the results that host code actually looks at."""
+
+    def __init__(self, engine_key="ite-resident", device: int = 0, arena_elems: int | None = None):
+        import os
+        self.eng = get_engine(engine_key, device)
+        if arena_elems is None:
+            arena_elems = int(float(os.environ.get("KBP_ITE_ARENA_GB", "8")) * (1 << 30) / 16)
+        self.arena_elems = arena_elems
+        self.p = Program(8)
+        self.eng.reserve(arena_elems, 1, 8)
+        self.eng._loaded = None
+        self.calls = 0
+
+    # ---------------------------------------------------------------- plumbing
+    def _flush(self):
+        if self.p.words:
+            if self.p.peak + 64 > self.arena_elems:
+                raise MemoryError(f"resident ITE arena too small ({self.arena_elems} elements): set KBP_ITE_ARENA_GB")
+            self.eng.run(np.array(self.p.words, dtype=np.int64), soft_errors=(-4,))
+            self.p.words = []
+            self.calls += 1
+
+    def put(self, a) -> RArr:
+        a = np.ascontiguousarray(a, dtype=np.complex128)
+        t = self.p.new(a.shape if a.ndim else (1,))
+        if self.p.peak + 64 > self.arena_elems:
+            raise MemoryError(f"resident ITE arena too small ({self.arena_elems} elements): set KBP_ITE_ARENA_GB")
+        if a.size:
+            self.eng.upload(t.off, a.reshape(-1), chain=0)
+        return RArr(self, t)
+
+    def _dt(self, x):
+        return x.dt if isinstance(x, RArr) else self.put(x).dt
+
+    def to_host(self, x: RArr) -> np.ndarray:
+        self._flush()
+        if x.size == 0:
+            return np.zeros(x.shape, dtype=np.complex128)
+        return self.eng.download(x.dt.off, x.size, chain=0).reshape(x.shape)
+
+    # ---------------------------------------------------------------- data movement
+    def reshape(self, a, shape):
+        if not isinstance(a, RArr):
+            return np.reshape(np.asarray(a), shape)
+        shape = tuple(int(s) for s in (shape if not isinstance(shape, int) else (shape,)))
+        if -1 in shape:
+            known = int(np.prod([s for s in shape if s != -1]))
+            shape = tuple(a.size // known if s == -1 else s for s in shape)
+        return RArr(self, a.dt.reshape(shape))
+
+    def transpose(self, a, perm):
+        if not isinstance(a, RArr):
+            return np.transpose(np.asarray(a), perm)
+        out = RArr(self, self.p.transpose(a.dt, perm))
+        self._flush()
+        return out
+
+    # ---------------------------------------------------------------- device ops
+    def tensordot(self, a, b, axes, conj_a=False, conj_b=False):
+        A, Bt = self._dt(a), self._dt(b)
+        if isinstance(axes, int):
+            assert axes == 0
+            c = self.p.matmul(A.reshape(A.size, 1), Bt.reshape(1, Bt.size), A.size, Bt.size, 1, 3 if conj_a else 0, 3 if conj_b else 0)
+            out = RArr(self, c.reshape(A.shape + Bt.shape))
+        else:
+            ax = (tuple(int(x) for x in axes[0]), tuple(int(x) for x in axes[1]))
+            out = RArr(self, self.p.tensordot(A, Bt, ax, conj_a=conj_a, conj_b=conj_b))
+        self._flush()
+        return out
+
+    def scale(self, a, s):
+        A = self._dt(a)
+        c = self.p.matmul(A.reshape(A.size, 1), self.put(np.array([[s]], dtype=np.complex128)).dt, A.size, 1, 1)
+        out = RArr(self, c.reshape(A.shape))
+        self._flush()
+        return out
+
+    def lincomb(self, a, alpha, b, beta):
+        A, Bt = self._dt(a), self._dt(b)
+        shape = A.shape
+        c = shape[-1]
+        r = A.size // c
+        coef = self.put(np.concatenate([alpha * np.eye(c), beta * np.eye(c)], axis=0))
+        z = self.p.zeros((r, 1, 2 * c))
+        self.p.embed(z, (0, 0, 0), A.reshape(r, 1, c))
+        self.p.embed(z, (0, 0, c), Bt.reshape(r, 1, c))
+        out = RArr(self, self.p.matmul(z.reshape(r, 2 * c), coef.dt, r, c, 2 * c).reshape(shape))
+        self._flush()
+        return out
+
+    def hermitize(self, m):
+        M = self._dt(m)
+        mh = RArr(self, self.p.transpose(M, (1, 0), conj=True))
+        return self.lincomb(RArr(self, M), 0.5, mh, 0.5)
+
+    def norm(self, a) -> float:
+        A = self._dt(a)
+        if A.size == 0:
+            return 0.0
+        self._flush()
+        self.eng.slots_zero()
+        x = self.p.copy(A)
+        self.p.normalize_(x, 0)
+        self._flush()
+        v = float(self.eng.slots()[0, 0])
+        if v == 0.0:                       # |a| = 1 exactly or a = 0: tell them apart on the host (tiny)
+            return float(np.linalg.norm(self.to_host(RArr(self, A))))
+        return math.exp(v)
+
+    def qr(self, m):
+        q, r = self.p.qr(self._dt(m))
+        self._flush()
+        return RArr(self, q), RArr(self, r)
+
+    def _svd_raw(self, m):
+        M = self._dt(m)
+        k = min(M.shape)
+        us, vh = self.p.svd_trunc(M, k, False, 0, 1, warm=False)
+        g = self.p.matmul(us, us, k, k, M.shape[0], 2, 0)
+        self._flush()
+        s = np.sqrt(np.maximum(np.real(np.diag(self.to_host(RArr(self, g)))), 0.0))
+        return RArr(self, us), s, RArr(self, vh)
+
+    def svd(self, m):
+        us, s, vh = self._svd_raw(m)
+        inv = np.where(s > 0, 1.0 / np.where(s > 0, s, 1.0), 0.0)
+        return self.tensordot(us, np.diag(inv).astype(np.complex128), ([1], [0])), s, vh
+
+    def eigh(self, h):
+        H = self._dt(h)
+        n = H.shape[0]
+        nrm = self.norm(RArr(self, H))
+        if not nrm > 0.0:
+            return np.zeros(n), np.eye(n, dtype=np.complex128)
+        m = self.lincomb(RArr(self, H), 1.0 / nrm, np.eye(n, dtype=np.complex128), _EIG_SHIFT)
+        us, s, vh = self._svd_raw(m)
+        w = (s - _EIG_SHIFT) * nrm
+        order = np.argsort(w, kind="stable")
+        return w[order], np.conj(self.to_host(vh)[order]).T

@@ -10,10 +10,10 @@ pytestmark = pytest.mark.gpu
 EDGES = ("AB", "AC", "BA", "BC", "CA", "CB")
 
 
-@pytest.fixture(scope="module")
-def B():
-    from kagomeperiodicbp_b200.linalg import DeviceBackend
-    return DeviceBackend()
+@pytest.fixture(scope="module", params=["per-call", "resident"])
+def B(request):
+    from kagomeperiodicbp_b200.linalg import DeviceBackend, ResidentBackend
+    return DeviceBackend() if request.param == "per-call" else ResidentBackend("ite-test-resident", arena_elems=1 << 26)
 
 
 def _inputs(g, key):
@@ -35,10 +35,10 @@ def test_backend_primitives(B):
     rng = np.random.default_rng(5)
     a = rng.normal(size=(7, 5, 6)) + 1j * rng.normal(size=(7, 5, 6))
     b = rng.normal(size=(6, 5, 3)) + 1j * rng.normal(size=(6, 5, 3))
-    assert np.allclose(B.tensordot(a, b, ([1, 2], [1, 0]), conj_b=True), np.tensordot(a, np.conj(b), axes=([1, 2], [1, 0])), atol=1e-13)
-    assert np.allclose(B.tensordot(np.eye(2), a[:2, :2, 0], 0), np.tensordot(np.eye(2), a[:2, :2, 0], 0), atol=1e-14)
+    assert np.allclose(np.asarray(B.tensordot(a, b, ([1, 2], [1, 0]), conj_b=True)), np.tensordot(a, np.conj(b), axes=([1, 2], [1, 0])), atol=1e-13)
+    assert np.allclose(np.asarray(B.tensordot(np.eye(2), a[:2, :2, 0], 0)), np.tensordot(np.eye(2), a[:2, :2, 0], 0), atol=1e-14)
     assert abs(B.norm(a) - np.linalg.norm(a)) < 1e-12
-    assert np.allclose(B.scale(a, 0.3 - 2j), a * (0.3 - 2j), atol=1e-13)
+    assert np.allclose(np.asarray(B.scale(a, 0.3 - 2j)), a * (0.3 - 2j), atol=1e-13)
     h = rng.normal(size=(36, 36)) + 1j * rng.normal(size=(36, 36))
     h = h + h.conj().T
     h[:, 5] = 0
@@ -49,11 +49,14 @@ def test_backend_primitives(B):
     assert np.linalg.norm(u.conj().T @ u - np.eye(36)) < 1e-12
     m = rng.normal(size=(12, 8)) + 1j * rng.normal(size=(12, 8))
     u, s, vh = B.svd(m)
+    u, vh = np.asarray(u), np.asarray(vh)
     assert np.allclose(s, np.linalg.svd(m, compute_uv=False), atol=1e-13)
     assert np.linalg.norm((u * s) @ vh - m) < 1e-13 * np.linalg.norm(m)
     q, r = B.qr(m)
-    assert np.linalg.norm(q @ r - m) < 1e-13 * np.linalg.norm(m)
-    assert np.allclose(B.hermitize(m[:8]), 0.5 * (m[:8] + m[:8].conj().T), atol=1e-14)
+    assert np.linalg.norm(np.asarray(q) @ np.asarray(r) - m) < 1e-13 * np.linalg.norm(m)
+    assert np.allclose(np.asarray(B.hermitize(m[:8])), 0.5 * (m[:8] + m[:8].conj().T), atol=1e-14)
+    x = B.transpose(B.tensordot(a, b, ([2], [0])), (3, 1, 0, 2))
+    assert np.allclose(np.asarray(B.reshape(x, (3 * 5, -1))), np.tensordot(a, b, axes=([2], [0])).transpose(3, 1, 0, 2).reshape(15, -1), atol=1e-13)
 
 
 @pytest.mark.parametrize("mode", "ABC")

@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   double* diag0 = reinterpret_cast<double*>(S + (size_t)b * ld);   // original diagonal
   double* dinv = diag0 + b;                                        // 1 / R_jj (0 for dropped columns)
   __shared__ double sh_min;
+  __shared__ cplx rowbuf[4 * CNB];                                 // [parity][row line | column line]
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
   const cplx* G = cb + G_;
-  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, w = t >> 5;
+  const int t = threadIdx.x, nt = blockDim.x;
   for (int e = t; e < b * b; e += nt) {
     cplx v = G[e];
     for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, G[(long long)sp * b * b + e]);
@@ -95,67 +96,78 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   if (t == 0) sh_min = 1.0;
   __syncthreads();
 
+#ifdef KBP_CHOL_TIMING
+  long long tA = 0, tB = 0, tC = 0, tL = 0, tF = 0, t_start = clock64(), tt0;
+#define TICK() tt0 = clock64()
+#define TOCK(acc) acc += clock64() - tt0
+#else
+#define TICK()
+#define TOCK(acc)
+#endif
   for (int p0 = 0; p0 < b; p0 += CNB) {
     const int p1 = p0 + CNB < b ? p0 + CNB : b, pw = p1 - p0;
-    // ---- phase A (warp 0): factor the diagonal block, then invert it.  Lane -> (row i = lane / 2, 8 columns): fixed
-    //      mapping, no index arithmetic in the 16 dependent pivot steps
-    if (w == 0) {
+    TICK();
+    // ---- phase A (8 warps, one thread per entry of the 16 x 16 diagonal block, entry kept in a register): 16 pivot steps,
+    //      the pivot row / column published through a double-buffered 2 x 16 shared-memory line and ONE 256-thread named
+    //      barrier per step; then the inverse of the block, 15 steps of (term per thread, half-warp shuffle sum).  A single
+    //      warp doing this alone is ~5x slower: nothing hides its dependent-issue latency.
+    if (t < 256) {
+      const int row = t >> 4, col = t & 15;
+      const bool in = row < pw && col < pw;
+      cplx v = in ? S[(p0 + row) * ld + p0 + col] : cmake(row == col ? 1.0 : 0.0, 0.0);
+      if (col < row) v = cconj(in ? S[(p0 + col) * ld + p0 + row] : cmake(0.0, 0.0));   // Hermitian: fill the lower part
       double mn = 1.0;
-      const int li = p0 + (lane >> 1), lc0 = p0 + (lane & 1) * 8;
-      for (int j = p0; j < p1; ++j) {
-        const double d = S[j * ld + j].x, d0 = diag0[j];
+      for (int j = 0; j < CNB; ++j) {
+        cplx* rb = rowbuf + (j & 1) * 2 * CNB;
+        cplx* cbuf = rb + CNB;
+        if (row == j) rb[col] = v;
+        if (col == j) cbuf[row] = v;
+        asm volatile("bar.sync 1, 256;");
+        const double d = rb[j].x;
+        const double d0 = j < pw ? diag0[p0 + j] : 1.0;
         const bool live = d0 > 0.0 && d > TSVD_PIVOT_DEAD * d0;      // NaN -> dropped
         const double ip = live ? rsqrt(d) : 0.0;
-        if (live) mn = fmin(mn, d / d0);
-        __syncwarp();
-        if (li == j) {                                            // the two lanes of row j scale it
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int l = lc0 + u;
-            if (l > j && l < p1) S[j * ld + l] = cscale(S[j * ld + l], ip);
-            else if (l == j) { S[j * ld + j] = cmake(live ? d * ip : 0.0, 0.0); dinv[j] = ip; }
-          }
-        }
-        __syncwarp();
-        if (li > j && li < p1) {
-          const cplx rji = S[j * ld + li];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int l = lc0 + u;
-            if (l >= li && l < p1) {
-              const cplx v = ccmul(rji, S[j * ld + l]);
-              cplx x = S[li * ld + l];
-              x.x -= v.x; x.y -= v.y;
-              if (l == li) x.y = 0.0;
-              S[li * ld + l] = x;
-            }
-          }
-        }
-        __syncwarp();
+        if (t == 0 && live && j < pw) mn = fmin(mn, d * __drcp_rn(d0));
+        const cplx srj = cbuf[row], sju = rb[col];                   // S[row][j], S[j][col]
+        const double ip2 = ip * ip;
+        const double vx = (srj.x * sju.x - srj.y * sju.y) * ip2, vy = (srj.x * sju.y + srj.y * sju.x) * ip2;
+        const bool below = row > j, right = col > j, mine = row == j;
+        double nx = v.x, ny = v.y;
+        nx = (below && right) ? nx - vx : nx;
+        ny = (below && right) ? ((col == row) ? 0.0 : ny - vy) : ny;
+        nx = (mine && right) ? nx * ip : nx;
+        ny = (mine && right) ? ny * ip : ny;
+        nx = (mine && col == j) ? (live ? d * ip : 0.0) : nx;
+        ny = (mine && col == j) ? 0.0 : ny;
+        v = cmake(nx, ny);
+        if (t == 0 && j < pw) dinv[p0 + j] = ip;
       }
-      if (lane == 0) sh_min = fmin(sh_min, mn);
-      // inverse of the diagonal block: lanes (2c, 2c+1) own column l = p0 + c and split the sums;  X[i][l] (i < l) is
-      // stored at S[l][i]
+      if (t == 0) sh_min = fmin(sh_min, mn);
+      if (in && col >= row) S[(p0 + row) * ld + p0 + col] = v;       // R (upper)
+      asm volatile("bar.sync 1, 256;");
+      // inverse X = R^{-1} of the block: thread (l = t >> 4, r = t & 15) holds x_rl;  x_il = -dinv_i sum_{r = i+1..l} R[i][r] x_rl
       {
-        const int l = p0 + (lane >> 1), half = lane & 1;
-        const bool act = l < p1;
-        const double xll = act ? dinv[l] : 0.0;
-        for (int i = p1 - 2; i >= p0; --i) {
-          cplx acc = cmake(0.0, 0.0);
-          if (act && i < l) {
-            if (half == 0) acc = cscale(S[i * ld + l], xll);              // R[i][l] x_ll
-            for (int r = i + 1 + half; r < l; r += 2) acc = cfma(S[i * ld + r], S[l * ld + r], acc);
+        const int l = t >> 4, rr = t & 15;
+        const bool act = l < pw && rr < pw;
+        cplx x = (act && rr == l) ? cmake(dinv[p0 + l], 0.0) : cmake(0.0, 0.0);
+        for (int i = CNB - 2; i >= 0; --i) {
+          cplx term = cmake(0.0, 0.0);
+          if (act && i < pw && rr > i && rr <= l) term = cmul(S[(p0 + i) * ld + p0 + rr], x);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
+            term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
           }
-          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
-          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-          if (act && i < l && half == 0) S[l * ld + i] = cscale(acc, -dinv[i]);
-          __syncwarp();
+          if (act && rr == i && i < l) x = cscale(term, -dinv[p0 + i]);
         }
+        if (act && rr < l) S[(p0 + l) * ld + p0 + rr] = x;             // X[rr][l] parked at S[l][rr]
       }
     }
     __syncthreads();
+    TOCK(tA);
     const int rem = b - p1;
     if (rem > 0) {
+      TICK();
       // ---- phase B: panel rows  R[r][l] = sum_{r' <= r} conj(X[r'][r]) S[r'][l],  l >= p1  (registers, then write)
       cplx outv[2];
       const int nel = pw * rem;
@@ -177,6 +189,8 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
         if (e < nel) S[(p0 + e / rem) * ld + p1 + e % rem] = outv[u];
       }
       __syncthreads();
+      TOCK(tB);
+      TICK();
       // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
       for (int e = t; e < rem * rem; e += nt) {
         const int i = p1 + e / rem, l = p1 + e % rem;
@@ -191,8 +205,10 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
         }
       }
       __syncthreads();
+      TOCK(tC);
     }
   }
+  TICK();
   if (R_ >= 0) {
     cplx* R = cb + R_;
     for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[(e / b) * ld + e % b] : cmake(0.0, 0.0);
@@ -257,6 +273,10 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
     Rinv[e] = i < l ? S[l * ld + i] : (i == l ? cmake(dinv[i], 0.0) : cmake(0.0, 0.0));
   }
   if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], sh_min);
+#ifdef KBP_CHOL_TIMING
+  TOCK(tL);
+  if (t == 0) printf("[chol b=%d] total %lld  A %lld (factor %lld)  B %lld  C %lld  levels+io %lld cycles\n", b, clock64() - t_start, tA, tF, tB, tC, tL);
+#endif
 }
 
 // How far span(Vh) is from an invariant subspace of A^H A, and the discarded weight, in two launches.

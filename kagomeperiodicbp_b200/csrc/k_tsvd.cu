@@ -463,10 +463,13 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     attr_set = true;
   }
   static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 5;
+  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
   static const int it_warm = getenv("KBP_TSVD_ITWARM") ? atoi(getenv("KBP_TSVD_ITWARM")) : 2;
   static const int it_step = getenv("KBP_TSVD_ITSTEP") ? atoi(getenv("KBP_TSVD_ITSTEP")) : 3;
-  static const int it_max = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 24;
+  // a block narrower than 2.5 keep (shared-memory cap of the b x b kernels, e.g. D = 6: keep 72, b 112) converges more slowly:
+  // more iterations are still far cheaper than the exact path on a (chi D^2)^2 matrix
+  static const int it_max_env = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 0;
+  const int it_max = it_max_env > 0 ? it_max_env : (2 * b >= 5 * keep ? 24 : 72);
   // warm start from the previous run's Ritz basis is opt-in: across BP iterations the message tensors keep changing gauge
   // in their (physically irrelevant) near-null directions, which makes the stored basis stale more often than not
   static const bool no_warm = getenv("KBP_TSVD_WARM") == nullptr || atoi(getenv("KBP_TSVD_WARM")) == 0;

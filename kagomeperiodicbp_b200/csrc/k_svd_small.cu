@@ -19,6 +19,7 @@
 #include "kbp_ops.cuh"
 
 #include <math.h>
+#include <stdio.h>
 
 namespace kbp {
 
@@ -75,13 +76,15 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
   }
   const double r2 = fma(cr, cr, ci * ci);
   if (!(a > floor2 && b > floor2 && r2 > 0.0)) return;
-  const double off = sqrt(r2 / (a * b));
-  my_off = fmax(my_off, off);
-  if (!(off > SMALL_TOL)) return;
-  const double ab = sqrt(r2), inv = 1.0 / ab;
+  // the pair counts as unconverged iff |c|^2 > tol^2 a b (no division / square root on the decision path); the rotation
+  // needs three dependent special-function evaluations: rsqrt(|c|^2) || rsqrt(d^2 + 4|c|^2), a reciprocal, rsqrt(1 + t^2)
+  if (!(r2 > (SMALL_TOL * SMALL_TOL) * a * b)) return;
+  my_off = 1.0;
+  const double inv = rsqrt(r2), ab = r2 * inv;
   const double er = cr * inv, ei = ci * inv;
   const double d = a - b;
-  double tt = 2.0 * ab / (fabs(d) + sqrt(fma(d, d, 4.0 * r2)));
+  const double h = fma(d, d, 4.0 * r2);
+  double tt = 2.0 * ab * __drcp_rn(fabs(d) + h * rsqrt(h));
   if (d < 0.0) tt = -tt;
   const double cs = rsqrt(fma(tt, tt, 1.0)), sn = tt * cs;
   const bool swap = d < 0.0;
@@ -143,7 +146,14 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   // groups of one warp can take different branches (phantom row, dead rows): shuffles name their own group only
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
   bool converged = p < 2;
+#ifdef KBP_SMALL_DEBUG
+  int nsweeps = 0;
+  long long tstart = clock64();
+#endif
   for (int sweep = 0; sweep < SMALL_MAX_SWEEPS && !converged; ++sweep) {
+#ifdef KBP_SMALL_DEBUG
+    ++nsweeps;
+#endif
     double my_off = 0.0;
     for (int step = 0; step < pp - 1; ++step) {
       if (slot < npairs) {
@@ -179,15 +189,15 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
           }
           const double r2 = fma(cr, cr, ci * ci);
           if (a > floor2 && b > floor2 && r2 > 0.0) {
-            const double off = sqrt(r2 / (a * b));
-            my_off = fmax(my_off, off);
-            if (off > SMALL_TOL) {
+            if (r2 > (SMALL_TOL * SMALL_TOL) * a * b) {
+              my_off = 1.0;
               // x_j' = e x_j with e = c/|c| makes <x_i, x_j'> = |c| real; then a real rotation by theta,
               // tan(2 theta) = 2|c| / (a - b), small-angle root
-              const double ab = sqrt(r2), inv = 1.0 / ab;
+              const double inv = rsqrt(r2), ab = r2 * inv;
               const double er = cr * inv, ei = ci * inv;
               const double d = a - b;
-              double tt = 2.0 * ab / (fabs(d) + sqrt(fma(d, d, 4.0 * r2)));
+              const double h = fma(d, d, 4.0 * r2);
+              double tt = 2.0 * ab * __drcp_rn(fabs(d) + h * rsqrt(h));
               if (d < 0.0) tt = -tt;
               const double cs = rsqrt(fma(tt, tt, 1.0)), sn = tt * cs;
               const bool swap = d < 0.0;            // keep the larger row first
@@ -215,7 +225,10 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
       if (lane == 0) sh_flag = x;
     }
     __syncthreads();
-    converged = sh_flag <= SMALL_TOL;
+    converged = sh_flag <= SMALL_TOL;      // (my_off is 1 for a lane group that rotated in this sweep, else 0)
+#ifdef KBP_SMALL_DEBUG
+    if (t == 0) printf("[small %dx%d] sweep %d max off %.3e  cycles %lld\n", p, q, sweep, sh_flag, clock64() - tstart);
+#endif
   }
 
   // ---- singular values = row norms, rank sort (descending, stable)

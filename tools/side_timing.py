@@ -1,0 +1,35 @@
+"""How much do the six concurrent side chains slow each other down?  Times one BP iteration (device resident) with 1, 2, 3, 6
+sides active.  usage: python tools/side_timing.py D N"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from kagomeperiodicbp_b200 import belief_propagation as bp
+from kagomeperiodicbp_b200.containers import BPConfig, UnitCell
+from kagomeperiodicbp_b200.lattice import BLOCK_SIDES_CCW
+from kagomeperiodicbp_b200.runtime import get_engine
+
+D, N = int(sys.argv[1]), int(sys.argv[2])
+cfg = BPConfig(trunc_dim=2 * D * D, msg_diff_terminate=1e-6, damping=0.1, init_msg="UQ")
+cell = UnitCell.random(2, D, seed=0)
+msgs = bp.initial_messages(D, N, "UQ")
+for _ in range(3):
+    out, msgs, err, _ = bp.bp_step_batch(N, [cell], [msgs], cfg)[0]
+shapes = bp._msg_shapes(msgs)
+comps = {s: bp.compile_side_program(N, 2, D, s, 2 * D * D, shapes, 0.1) for s in BLOCK_SIDES_CCW}
+engs = {s: get_engine(("side", s), 0) for s in BLOCK_SIDES_CCW}
+for s in BLOCK_SIDES_CCW:
+    comps[s].load(engs[s], 1)
+    engs[s].upload(0, comps[s].pack_inputs([bp._side_inputs(cell, msgs, comps[s])]))
+    engs[s].sync()
+for k in (1, 2, 3, 6):
+    sides = BLOCK_SIDES_CCW[:k]
+    best = 1e9
+    for rep in range(3):
+        t0 = time.perf_counter()
+        futs = [bp._pool.submit(comps[s].run_resident, engs[s], (-4,)) for s in sides]
+        for f in futs:
+            f.result()
+        for s in sides:
+            engs[s].sync()
+        best = min(best, time.perf_counter() - t0)
+    print(f"{k} side(s) concurrently: {best*1e3:.1f} ms per iteration")

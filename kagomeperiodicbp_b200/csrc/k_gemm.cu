@@ -5,7 +5,7 @@
 // BM x BN tile with 8 warps and streams its k-slabs through a 4-stage cp.async ring in shared memory
 // (16-byte copies of whole complex128 elements, zero-filled past the edges), one barrier per slab.
 // Tiles are 64x64 (warps 4 x 2, four 16x8 accumulators each) when that already fills the machine, else
-// 32x32 (warps 2 x 4); products with a long k and a tiny output (Gram matrices Y^H Y) can additionally be
+// 32x32 (warps 2 x 4), else 16x16 (2 warps); products with a long k and a tiny output (Gram matrices Y^H Y) can additionally be
 // split along k into `ksplit` partial results written side by side (summed by the consumer: deterministic,
 // no atomics).  Operands stay in the layout they have in HBM -- "k-contiguous" [row][k] or
 // "m-contiguous" [k][row] depending on op -- so every copy is coalesced and transposition / conjugation
@@ -14,6 +14,8 @@
 //     Cr += Ar*Br - Ai*Bi ;  Ci += Ar*Bi + Ai*Br.
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
+
+#include <stdlib.h>
 
 namespace kbp {
 
@@ -25,7 +27,13 @@ struct GemmArgs {
   int m, n, k, opA, opB;
   int ksplit;                     // partial results: C + s * m * n, s < ksplit
   int rows_on_x;                  // grid.x (2^31 limit) carries the row tiles instead of the column tiles
+  int fused;                      // ksplit > 1 only: partials go to the scratch area and the LAST CTA of every tile adds them up
+  double2* scratch;               // [nb][scratch_stride]
+  long long scratch_stride;
+  int* counters;                  // [nb][GEMM_MAX_TILES], zero between launches
 };
+
+constexpr int GEMM_MAX_TILES = 4096;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -36,9 +44,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int BM, int BN, int STAGES>
-__global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base, long long chain_stride, GemmArgs g) {
-  constexpr int WMS = BM / 16, WNS = 8 / WMS;    // warp grid
+template <int BM, int BN, int STAGES, int NWARPS>
+__global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restrict__ base, long long chain_stride, GemmArgs g) {
+  constexpr int NTHR = 32 * NWARPS;
+  constexpr int WMS = BM / 16, WNS = NWARPS / WMS;    // warp grid
   constexpr int NT = BN / WNS / 8;               // 16x8 accumulator tiles per warp
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);   // elements per A tile (either layout)
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
@@ -72,8 +81,8 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
     cplx* at = As + stage * TA;
     cplx* bt = Bs + stage * TB;
 #pragma unroll
-    for (int r = 0; r < BM * BK / 256; ++r) {
-      const int c = t + 256 * r;
+    for (int r = 0; r < BM * BK / NTHR; ++r) {
+      const int c = t + NTHR * r;
       if (a_kc) {
         const int mm = c / BK, kk = c % BK;
         const bool ok = row0 + mm < g.m && k0 + kk < g.k;
@@ -85,8 +94,8 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
       }
     }
 #pragma unroll
-    for (int r = 0; r < BN * BK / 256; ++r) {
-      const int c = t + 256 * r;
+    for (int r = 0; r < BN * BK / NTHR; ++r) {
+      const int c = t + NTHR * r;
       if (b_kc) {
         const int nn = c / BK, kk = c % BK;
         const bool ok = col0 + nn < g.n && k0 + kk < g.k;
@@ -99,11 +108,17 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
     }
   };
 
-  double cr[NT][4], ci[NT][4];
+  // FP64 DMMA has a long dependent-issue latency: with one accumulator tile per warp (the small-tile configurations) the
+  // four products of a complex MAC and consecutive k8 steps would form one serial chain per slab.  They get independent
+  // accumulators (2 products x 2 k8 parities) that are added up in the epilogue.
+  constexpr int NACC = (NT <= 2) ? 4 : 1;
+  double cr[NACC][NT][4], ci[NACC][NT][4];
 #pragma unroll
-  for (int i = 0; i < NT; ++i)
+  for (int q4 = 0; q4 < NACC; ++q4)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cr[i][j] = ci[i][j] = 0.0;
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cr[q4][i][j] = ci[q4][i][j] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -138,51 +153,121 @@ __global__ void __launch_bounds__(256) zgemm_dmma_kernel(cplx* __restrict__ base
           br[v] = x.x;
           bi[v] = sb * x.y;
         }
-        dmma16x8x8(cr[nt], ar, br);
-        dmma16x8x8(cr[nt], an, bi);
-        dmma16x8x8(ci[nt], ar, bi);
-        dmma16x8x8(ci[nt], aim, br);
+        constexpr int A1 = NACC == 4 ? 1 : 0;
+        const int a0 = NACC == 4 ? 2 * (ks & 1) : 0;
+        dmma16x8x8(cr[a0][nt], ar, br);
+        dmma16x8x8(cr[a0 + A1][nt], an, bi);
+        dmma16x8x8(ci[a0][nt], ar, bi);
+        dmma16x8x8(ci[a0 + A1][nt], aim, br);
       }
     }
   }
   cp_async_wait<0>();
+  if (g.fused) {
+    // split-K without a second launch: every CTA parks its partial tile, the last one to arrive at the tile's counter adds
+    // the ksplit partials in fixed order (bitwise deterministic) and writes C
+    __shared__ int sh_last;
+    cplx* part = g.scratch + (long long)chain * g.scratch_stride;
+    const long long mn = (long long)g.m * g.n;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int r = row0 + wm * 16 + gq + 8 * (v >> 1);
+        const int c = col0 + wn * (NT * 8) + nt * 8 + 2 * q + (v & 1);
+        double sr = cr[0][nt][v], si = ci[0][nt][v];
+#pragma unroll
+        for (int q4 = 1; q4 < NACC; ++q4) { sr += cr[q4][nt][v]; si += ci[q4][nt][v]; }
+        if (r < g.m && c < g.n) part[split * mn + (long long)r * g.n + c] = cmake(sr, si);
+      }
+    __threadfence();
+    __syncthreads();
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    if (t == 0) sh_last = atomicAdd(g.counters + chain * GEMM_MAX_TILES + tile, 1) == g.ksplit - 1;
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    Cb = base + (long long)chain * chain_stride + g.C;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int r = row0 + wm * 16 + gq + 8 * (v >> 1);
+        const int c = col0 + wn * (NT * 8) + nt * 8 + 2 * q + (v & 1);
+        if (r < g.m && c < g.n) {
+          double sr = 0.0, si = 0.0;
+          for (int sp = 0; sp < g.ksplit; ++sp) {
+            const cplx x = __ldcg(part + sp * mn + (long long)r * g.n + c);
+            sr += x.x; si += x.y;
+          }
+          Cb[(long long)r * g.n + c] = cmake(sr, si);
+        }
+      }
+    if (t == 0) g.counters[chain * GEMM_MAX_TILES + tile] = 0;
+    return;
+  }
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int r = row0 + wm * 16 + gq + 8 * (v >> 1);
       const int c = col0 + wn * (NT * 8) + nt * 8 + 2 * q + (v & 1);
-      if (r < g.m && c < g.n) Cb[(long long)r * g.n + c] = cmake(cr[nt][v], ci[nt][v]);
+      double sr = cr[0][nt][v], si = ci[0][nt][v];
+#pragma unroll
+      for (int q4 = 1; q4 < NACC; ++q4) { sr += cr[q4][nt][v]; si += ci[q4][nt][v]; }
+      if (r < g.m && c < g.n) Cb[(long long)r * g.n + c] = cmake(sr, si);
     }
 }
 
-template <int BM, int BN, int STAGES>
+template <int BM, int BN, int STAGES, int NWARPS>
 static void launch_gemm(const Arena& a, GemmArgs g) {
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
   constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   const unsigned tn = (unsigned)((g.n + BN - 1) / BN), tm = (unsigned)((g.m + BM - 1) / BM);
   g.rows_on_x = tm > tn;
   dim3 grid(g.rows_on_x ? tm : tn, g.rows_on_x ? tn : tm, (unsigned)(a.nb * g.ksplit));
-  zgemm_dmma_kernel<BM, BN, STAGES><<<grid, 256, smem, a.stream>>>(a.base, a.chain_stride, g);
+  zgemm_dmma_kernel<BM, BN, STAGES, NWARPS><<<grid, 32 * NWARPS, smem, a.stream>>>(a.base, a.chain_stride, g);
   ++*a.launches;
 }
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
   if (m == 0 || n == 0) return;
-  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0};
+  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev};
+  if (ksplit == 0) {
+    // automatic: a small product is bound by how many warps (16x8 accumulator tiles) it offers to the 592 sub-partitions;
+    // split k (fused, deterministic reduction) until there are enough, keeping >= 4 slabs per split
+    const int64_t tiles16 = ((n + 15) / 16) * ((m + 15) / 16);
+    const int64_t warps = 2 * tiles16 * a.nb;
+    const int64_t slabs = (k + BK - 1) / BK;
+    int ks = 1;
+    static const bool no_auto = getenv("KBP_GEMM_NOSPLIT") != nullptr;
+    if (!no_auto && warps < 600 && slabs >= 8 && tiles16 <= GEMM_MAX_TILES && a.scratch != nullptr) {
+      ks = (int)((900 + warps - 1) / warps);
+      if (ks > slabs / 4) ks = (int)(slabs / 4);
+      if (ks > 16) ks = 16;
+      while (ks > 1 && (int64_t)ks * m * n > a.scratch_stride) --ks;
+    }
+    g.ksplit = ks < 1 ? 1 : ks;
+    g.fused = g.ksplit > 1;
+  }
+  // FP64 DMMA runs at 64 FMA/clk/SM: a 32x32 tile needs ~1000 cycles per 16-deep k-slab, so a product that covers only a
+  // few dozen tiles is bound by the handful of SMs it occupies.  Pick the largest tile that still spreads over the machine.
   const int64_t ctas64 = ((n + 63) / 64) * ((m + 63) / 64) * a.nb * g.ksplit;
-  if (ctas64 >= 96) launch_gemm<64, 64, 3>(a, g);
-  else launch_gemm<32, 32, 4>(a, g);
+  const int64_t ctas32 = ((n + 31) / 32) * ((m + 31) / 32) * a.nb * g.ksplit;
+  if (g.fused) launch_gemm<16, 16, 4, 2>(a, g);
+  else if (ctas64 >= 96) launch_gemm<64, 64, 3, 8>(a, g);
+  else if (ctas32 >= 96) launch_gemm<32, 32, 4, 8>(a, g);
+  else launch_gemm<16, 16, 4, 2>(a, g);
 }
 
 void gemm(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB) {
-  gemm_splitk(a, C, A, B, m, n, k, opA, opB, 1);
+  gemm_splitk(a, C, A, B, m, n, k, opA, opB, 0);
 }
 
 }  // namespace kbp

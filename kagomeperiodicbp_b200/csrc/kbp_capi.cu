@@ -11,6 +11,8 @@
 
 #include "kbp_ops.cuh"
 
+static const int64_t KBP_GEMM_SCRATCH = 1 << 20;   // complex128 elements per chain for split-K partial tiles (16 MB)
+
 struct kbp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -19,6 +21,8 @@ struct kbp_ctx {
   int nb = 0;
   double* slots = nullptr;
   int n_slots = 0;
+  double2* scratch = nullptr;
+  int* counters_dev = nullptr;
   double* svd_off = nullptr;
   double* svd_off_host = nullptr;
   int64_t launches = 0;
@@ -74,6 +78,9 @@ int kbp_create(int device, kbp_ctx** out) {
 static void free_arena(kbp_ctx* c) {
   if (c->arena) cudaFree(c->arena);
   if (c->slots) cudaFree(c->slots);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->counters_dev) cudaFree(c->counters_dev);
+  c->scratch = nullptr; c->counters_dev = nullptr;
   if (c->svd_off) cudaFree(c->svd_off);
   if (c->svd_off_host) cudaFreeHost(c->svd_off_host);
   c->arena = nullptr; c->slots = nullptr; c->svd_off = nullptr; c->svd_off_host = nullptr;
@@ -101,6 +108,9 @@ int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
     free_arena(c);
     CU(c, cudaMalloc(&c->arena, sizeof(double2) * (size_t)chain_elems * nb));
     CU(c, cudaMalloc(&c->slots, sizeof(double) * (size_t)nb * n_slots));
+    CU(c, cudaMalloc(&c->scratch, sizeof(double2) * (size_t)KBP_GEMM_SCRATCH * nb));
+    CU(c, cudaMalloc(&c->counters_dev, sizeof(int) * (size_t)4096 * nb));
+    CU(c, cudaMemsetAsync(c->counters_dev, 0, sizeof(int) * (size_t)4096 * nb, c->stream));
     CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)(6 + 32 * 160) * nb));
     CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * 4 * nb));
     c->chain_elems = chain_elems; c->nb = nb; c->n_slots = n_slots;
@@ -243,6 +253,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
   a.stream = c->stream; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };
   auto slot_ok = [&](int64_t s) { return s >= -1 && s < c->n_slots; };

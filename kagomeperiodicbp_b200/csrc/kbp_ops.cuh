@@ -17,6 +17,9 @@ struct Arena {
   int n_slots;
   int nb;
   cudaStream_t stream;
+  double2* scratch;       // split-K partial tiles: [nb][scratch_stride] complex128 (may be null)
+  int64_t scratch_stride;
+  int* counters_dev;      // split-K tile semaphores: [nb][4096] ints, zero between launches
   int64_t* launches;      // host counter of kernel launches
   int64_t* counters;      // host counters [8]: see svd_truncate
   std::unordered_map<long long, int>* warm;   // warm-start buffers that hold a valid Ritz basis: offset -> block size
@@ -40,7 +43,8 @@ void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
                  int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm);
 int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep);
-// C partial sums side by side (C + s*m*n, s < ksplit), each over a contiguous range of k
+// ksplit >= 1: C partial sums side by side (C + s*m*n, s < ksplit), each over a contiguous range of k;  ksplit == 0: automatic
+// fused split (partials in the scratch area, last CTA per tile reduces) -- what gemm() does
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit);
 int64_t svd_work_elems(int64_t m, int64_t n);
 // buf /= ||buf||_F ; slot += ln ||buf||_F

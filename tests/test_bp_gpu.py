@@ -109,6 +109,17 @@ def test_d4_chain_properties():
             assert np.linalg.norm(M @ M.conj().T - np.eye(a.shape[0])) < 1e-9
         assert overlap_defect(o_out[side], m) < TOL
         assert overlap_defect(o_nxt[side], to_oracle_mps(nxt[side].mps)) < TOL
+        assert dense_rel_diff(o_out[side], m) < TOL                                # (16^3 entries: tractable at N = 2)
+    # second iteration: full-rank boundary-MPS spectra, i.e. the regime the subspace-iteration SVD is built for
+    before = {k: sum(bp.get_engine(("side", s)).svd_counters()[k] for s in SIDES) for k in ("subspace", "subspace_fallback")}
+    out2, nxt2, err2, _ = bp.bp_step_batch(N, [cell], [nxt], cfg)[0]
+    after = {k: sum(bp.get_engine(("side", s)).svd_counters()[k] for s in SIDES) for k in ("subspace", "subspace_fallback")}
+    assert after["subspace"] - before["subspace"] >= 80 and after["subspace_fallback"] - before["subspace_fallback"] <= 2
+    o_out2, o_nxt2, o_err2 = bp_np.bp_step(N, cell.tensors(), o_nxt, ocfg)
+    assert abs(err2 - o_err2) < 1e-8
+    for side in SIDES:
+        assert dense_rel_diff(o_out2[side], to_oracle_mps(out2[side].mps)) < TOL, side
+        assert dense_rel_diff(o_nxt2[side], to_oracle_mps(nxt2[side].mps)) < TOL, side
 
 
 def test_missing_device_path_is_loud():

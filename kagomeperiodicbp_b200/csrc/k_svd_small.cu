@@ -13,7 +13,8 @@
 //
 // Outputs (same contract as the block-Jacobi kernel in k_svd.cu):
 //   m <= n:  rows converge to s_i v_i^H ->  Vh_k = rows / s  (orthonormal to rounding),  US = A Vh_k^H
-//   m >  n:  rows converge to s_i u_i^T ->  US_k = rows,   Vh_k = diag(1/s^2) US_k^H A
+//   m >  n:  the rows carry an identity block behind them, [A^T | I], rotated along (Gram sums over the A^T part only):
+//            rows converge to [s_i u_i^T | conj(v_i)^T]  ->  US_k = first part, Vh_k = conj(second part), both exact
 // so US Vh is exactly the projection of A on the span found, whatever the rounding of the other factor.
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
@@ -42,19 +43,18 @@ struct SmallArgs {
 };
 
 size_t svd_small_smem(int64_t m, int64_t n) {
-  const int64_t p = m < n ? m : n, q = m < n ? n : m;
+  const int64_t p = m < n ? m : n, q = m <= n ? n : m + n;       // tall: rows of [A^T | I]
   return (size_t)(p * q) * sizeof(double2) + (size_t)p * (sizeof(double) + sizeof(int)) + 64;
 }
 
 bool svd_small_fits(int64_t m, int64_t n) {
-  // tall matrices (m > n) would need V = diag(1/s^2) US^H A, which loses (s_1/s_k) digits of orthonormality: they are
-  // rare on this path (reduceD reshapes sites as [D_left, d * D_right]) and go to the block-Jacobi kernel instead
-  return m <= n && m <= 128 && svd_small_smem(m, n) <= SMALL_SMEM_MAX;
+  const int64_t p = m < n ? m : n;
+  return p <= 128 && svd_small_smem(m, n) <= SMALL_SMEM_MAX;
 }
 
 // rotate one row pair with both rows held in registers between the Gram sums and the update (CPL columns per lane)
 template <int CPL>
-__device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int G, int gl, unsigned gmask,
+__device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int qx, int G, int gl, unsigned gmask,
                                                    double floor2, double& my_off) {
   cplx u[CPL], v[CPL];
   double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
@@ -63,10 +63,12 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
     const int c = gl + k * G;
     u[k] = c < q ? xi[c] : cmake(0.0, 0.0);
     v[k] = c < q ? xj[c] : cmake(0.0, 0.0);
-    a = fma(u[k].x, u[k].x, fma(u[k].y, u[k].y, a));
-    b = fma(v[k].x, v[k].x, fma(v[k].y, v[k].y, b));
-    cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));
-    ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
+    if (c < qx) {                                  // Gram sums over the data columns only (not the accumulated rotations)
+      a = fma(u[k].x, u[k].x, fma(u[k].y, u[k].y, a));
+      b = fma(v[k].x, v[k].x, fma(v[k].y, v[k].y, b));
+      cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));
+      ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
+    }
   }
   for (int o = G >> 1; o > 0; o >>= 1) {
     a += __shfl_xor_sync(gmask, a, o);
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int m = g.m, n = g.n;
   const bool mode_t = m > n;
-  const int p = mode_t ? n : m, q = mode_t ? m : n;
+  const int p = mode_t ? n : m, qx = mode_t ? m : n, q = mode_t ? m + n : n;   // q: row length incl. the identity block of a tall matrix
   cplx* X = reinterpret_cast<cplx*>(sm_raw);                                 // p x q
   double* s2 = reinterpret_cast<double*>(sm_raw + sizeof(cplx) * (size_t)p * q);   // p
   int* idx = reinterpret_cast<int*>(s2 + p);                                 // p
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
       X[c * q + r] = v;
       fro += cabs2(v);
     }
+    for (int e = t; e < n * n; e += nt) X[(e / n) * q + m + e % n] = cmake(e / n == e % n ? 1.0 : 0.0, 0.0);
   }
   const double fro2 = block_sum(fro, red);          // (contains the barrier that publishes X)
   const double floor2 = 1e-34 * fro2;
@@ -163,18 +166,18 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
           cplx* xi = X + i * q;
           cplx* xj = X + j * q;
           switch ((q + G - 1) / G) {
-            case 1: jacobi_pair_cached<1>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
-            case 2: jacobi_pair_cached<2>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
-            case 3: jacobi_pair_cached<3>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
-            case 4: jacobi_pair_cached<4>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
-            case 5: jacobi_pair_cached<5>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
-            default: jacobi_pair_cached<6>(xi, xj, q, G, gl, gmask, floor2, my_off); break;
+            case 1: jacobi_pair_cached<1>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+            case 2: jacobi_pair_cached<2>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+            case 3: jacobi_pair_cached<3>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+            case 4: jacobi_pair_cached<4>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+            case 5: jacobi_pair_cached<5>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+            default: jacobi_pair_cached<6>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
           }
         } else if (j < p) {
           cplx* xi = X + i * q;
           cplx* xj = X + j * q;
           double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
-          for (int c = gl; c < q; c += G) {
+          for (int c = gl; c < qx; c += G) {
             const cplx u = xi[c], v = xj[c];
             a = fma(u.x, u.x, fma(u.y, u.y, a));
             b = fma(v.x, v.x, fma(v.y, v.y, b));
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   for (int i = w; i < p; i += nw) {
     double acc = 0.0;
     const cplx* row = X + i * q;
-    for (int c = lane; c < q; c += 32) acc += cabs2(row[c]);
+    for (int c = lane; c < qx; c += 32) acc += cabs2(row[c]);
     acc = warp_sum(acc);
     if (lane == 0) s2[i] = (acc == acc && acc < 1e300) ? acc : 0.0;
   }
@@ -274,19 +277,14 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
       if (lane == 0) US[e] = sk2 > floor2 ? cscale(acc, rsqrt(sk2) * scale) : cmake(0.0, 0.0);
     }
   } else {
-    // US_k = rows ;  Vh_k = diag(1/s^2) US_k^H A
+    // US_k = data part of the rows ;  Vh_k = conj of the accumulated-rotation part (orthonormal to rounding)
     for (int e = t; e < m * keep; e += nt) {
       const int r = e / keep, k = e - r * keep;
       US[e] = cscale(X[idx[k] * q + r], scale);
     }
-    for (int e = w; e < keep * n; e += nw) {
+    for (int e = t; e < keep * n; e += nt) {
       const int k = e / n, c = e - k * n;
-      const double sk2 = s2[idx[k]];
-      const cplx* xr = X + idx[k] * q;
-      cplx acc = cmake(0.0, 0.0);
-      for (int r = lane; r < m; r += 32) acc = cadd(acc, ccmul(xr[r], A[(long long)r * g.lda + c]));
-      acc = warp_sum(acc);
-      if (lane == 0) Vh[e] = sk2 > floor2 ? cscale(acc, 1.0 / sk2) : cmake(0.0, 0.0);
+      Vh[e] = s2[idx[k]] > floor2 ? cconj(X[idx[k] * q + m + c]) : cmake(0.0, 0.0);
     }
   }
   if (t == 0) {
@@ -316,7 +314,7 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
   threads = (threads + 31) / 32 * 32;
   if (threads < 256) threads = 256;
   if (threads > 1024) threads = 1024;
-  const int q = (int)(m < n ? n : m);
+  const int q = (int)(m <= n ? n : m + n);
   if (threads <= 768 && (q + G - 1) / G <= 6)
     svd_small_kernel<true><<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
   else

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kbp_ops.cuh"
@@ -29,6 +30,9 @@ struct kbp_ctx {
   int64_t svd_sweeps = 0;
   int64_t counters[8] = {0};
   std::unordered_map<long long, int> warm;
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; bool bad = false; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of sync-free programs, keyed by a hash of the op stream
+  int64_t graph_replays = 0;
   bool profile = false;
   struct Span { int op; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -75,7 +79,14 @@ int kbp_create(int device, kbp_ctx** out) {
   return KBP_OK;
 }
 
+static void drop_graphs(kbp_ctx* c) {
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  c->graphs.clear();
+}
+
 static void free_arena(kbp_ctx* c) {
+  drop_graphs(c);
   if (c->arena) cudaFree(c->arena);
   if (c->slots) cudaFree(c->slots);
   if (c->scratch) cudaFree(c->scratch);
@@ -199,6 +210,7 @@ int64_t kbp_svd_sweeps(const kbp_ctx* c) { return c ? c->svd_sweeps : 0; }
 int kbp_svd_counters(const kbp_ctx* c, int64_t* out8) {
   if (!c || !out8) return KBP_E_ARG;
   for (int i = 0; i < 8; ++i) out8[i] = c->counters[i];
+  out8[6] = c->graph_replays;
   return KBP_OK;
 }
 
@@ -247,7 +259,95 @@ static inline double bits_to_double(int64_t b) {
   return d;
 }
 
+// op lengths (words after the opcode) for the pre-scan; -1: variable (permute)
+static bool program_is_sync_free(const int64_t* w, int64_t n_words, int64_t* n_ops) {
+  int64_t i = 0;
+  *n_ops = 0;
+  while (i < n_words) {
+    const int64_t op = w[i];
+    ++*n_ops;
+    switch (op) {
+      case KBP_OP_PERMUTE: {
+        if (i + 4 >= n_words) return false;
+        const int64_t nd = w[i + 4];
+        if (nd < 1 || nd > 8) return false;
+        i += 5 + 2 * nd;
+        break;
+      }
+      case KBP_OP_GEMM: i += 9; break;
+      case KBP_OP_QR: i += 7; break;
+      case KBP_OP_SVD:
+        if (i + 11 >= n_words) return false;
+        if (!kbp::svd_small_fits(w[i + 5], w[i + 6])) return false;      // other SVD paths read flags back on the host
+        i += 12;
+        break;
+      case KBP_OP_NORMALIZE: i += 4; break;
+      case KBP_OP_EMBED: i += 12; break;
+      case KBP_OP_ZERO: i += 3; break;
+      case KBP_OP_SCALAR_TO_SLOT: i += 4; break;
+      case KBP_OP_NONFINITE: i += 4; break;
+      case KBP_OP_EYE: i += 4; break;
+      default: return false;
+    }
+  }
+  return i == n_words;
+}
+
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words);
+
 int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
+  if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
+  static const bool graphs_on = !(getenv("KBP_GRAPHS") && atoi(getenv("KBP_GRAPHS")) == 0);
+  static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
+  int64_t n_ops = 0;
+  if (!graphs_on || c->profile || sync_every || n_words < 256 || !program_is_sync_free(w, n_words, &n_ops) || n_ops < 32)
+    return run_ops(c, w, n_words);
+  // A program whose truncations all take the in-shared-memory Jacobi kernel never looks at the device from the host: its
+  // launch sequence is a constant.  Second run: capture it; afterwards: one graph launch instead of hundreds of launches.
+  uint64_t h = 1469598103934665603ull;
+  for (int64_t i = 0; i < n_words; ++i) { h ^= (uint64_t)w[i]; h *= 1099511628211ull; }
+  h ^= (uint64_t)n_words * 0x9E3779B97F4A7C15ull;
+  auto it = c->graphs.find(h);
+  if (it == c->graphs.end()) {
+    if (c->graphs.size() >= 64) return run_ops(c, w, n_words);
+    it = c->graphs.emplace(h, kbp_ctx::GraphEntry()).first;
+  }
+  kbp_ctx::GraphEntry& ge = it->second;
+  CU(c, cudaSetDevice(c->device));
+  if (ge.exec) {
+    CU(c, cudaGraphLaunch(ge.exec, c->stream));
+    c->launches += ge.launches;
+    for (int k = 0; k < 8; ++k) c->counters[k] += ge.dcount[k];
+    ++c->graph_replays;
+    return KBP_OK;
+  }
+  if (ge.bad || ge.seen++ == 0) return run_ops(c, w, n_words);      // first run: plain (sets function attributes, warms up)
+  const int64_t l0 = c->launches;
+  int64_t c0[8];
+  for (int k = 0; k < 8; ++k) c0[k] = c->counters[k];
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { ge.bad = true; cudaGetLastError(); return run_ops(c, w, n_words); }
+  const int rc = run_ops(c, w, n_words);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e1 = cudaStreamEndCapture(c->stream, &graph);
+  if (rc != KBP_OK || e1 != cudaSuccess || !graph) {
+    ge.bad = true;
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    c->launches = l0;
+    for (int k = 0; k < 8; ++k) c->counters[k] = c0[k];
+    return run_ops(c, w, n_words);
+  }
+  const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) { ge.bad = true; ge.exec = nullptr; cudaGetLastError(); c->launches = l0; for (int k = 0; k < 8; ++k) c->counters[k] = c0[k]; return run_ops(c, w, n_words); }
+  ge.launches = c->launches - l0;
+  for (int k = 0; k < 8; ++k) ge.dcount[k] = c->counters[k] - c0[k];
+  CU(c, cudaGraphLaunch(ge.exec, c->stream));
+  ++c->graph_replays;
+  return KBP_OK;
+}
+
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;

@@ -43,6 +43,7 @@ void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
                  int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm);
 int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep);
+bool svd_small_fits(int64_t m, int64_t n);
 // ksplit >= 1: C partial sums side by side (C + s*m*n, s < ksplit), each over a contiguous range of k;  ksplit == 0: automatic
 // fused split (partials in the scratch area, last CTA per tile reduces) -- what gemm() does
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit);

@@ -88,7 +88,8 @@ def svd_warm_elems(m: int, n: int, keep: int) -> int:
     """size of the persistent Ritz-basis buffer of one truncation (0: the op never takes the subspace path).
     Mirrors kbp_svd_warm_elems / tsvd_block in k_tsvd.cu."""
     p = min(m, n)
-    if m <= n and m <= 128 and p * max(m, n) * 16 + p * 12 + 64 <= 225 * 1024:
+    q = n if m <= n else m + n
+    if p <= 128 and p * q * 16 + p * 12 + 64 <= 225 * 1024:
         return 0                                  # in-shared-memory Jacobi
     b = min(112, (keep * 25 // 10 + 7) // 8 * 8)
     if b < keep + 8 or b * 100 > p * 80:
@@ -182,7 +183,7 @@ class Engine:
         out = np.zeros(8, dtype=np.int64)
         self._check(self.lib.kbp_svd_counters(self.h, out.ctypes.data_as(ctypes.c_void_p)))
         return {"small": int(out[1]), "subspace": int(out[2]), "subspace_fallback": int(out[3]), "block_jacobi": int(out[4]),
-                "subspace_iterations": int(out[5])}
+                "subspace_iterations": int(out[5]), "graph_replays": int(out[6])}
 
     def profile_enable(self, on: bool):
         self._check(self.lib.kbp_profile_enable(self.h, 1 if on else 0))

@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--shard", default="cells", choices=("cells", "sides"),
                     help="N > 1: independent unit cells per rank (weak scaling, no collective) or the six sides of ONE cell "
                          "sharded over the ranks with one all-gather of the new messages per iteration (strong scaling)")
+    ap.add_argument("--ensemble", type=int, default=4, help="unit cells per launch for the extra ensemble measurement at N=1 (0 = skip)")
     ap.add_argument("--ite-steps", type=int, default=3, help="ITE steps (loop bodies of ite_per_mode) timed on rank 0 at N=1; 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
@@ -369,7 +370,12 @@ def main():
         # rate of the SVD family is its flops over the wall time of the step scaled by its share of op time
         share = svd_ms / max(1e-9, float(ms.sum()))
         achieved = svd_flops / (ms_step * 1e-3 * share) / 1e12
-        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the three kernels of the family, from the
+                            # `ncu --set full` capture summarised in profiles/r01_ncu_full_tsvd_kernels.csv and r01_SUMMARY.md
+                            # (cold L2; in the running step the operands are L2 resident: the family is not HBM bound)
+                            "traffic": 212480, "traffic_detail_bytes_per_launch": {"svd_small_kernel": 212480, "chol_inv_kernel": 465408,
+                                                                                   "zgemm_dmma_kernel<32,32>": 780544},
                             "kernel": "truncated-SVD family (zgemm_dmma_kernel + chol_inv_kernel + svd_small_kernel subspace iteration; svd_round_kernel fallback)",
                             "peak_source": "cuBLAS DGEMM 4096^3 FP64 measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
                             "algorithmic_flops_per_step": svd_flops, "svd_share_of_op_time": share,
@@ -379,6 +385,28 @@ def main():
                             "op_counts": {k: int(cnt[i]) for k, i in (("permute", 1), ("gemm", 2), ("qr", 3), ("svd", 4))},
                             "jacobi_sweeps_total": sum(engs[s].svd_sweeps() for s in BLOCK_SIDES_CCW),
                             "svd_paths": {k: sum(engs[s].svd_counters()[k] for s in BLOCK_SIDES_CCW) for k in engs[BLOCK_SIDES_CCW[0]].svd_counters()}}
+        if world == 1 and a.ensemble > 1 and B == 1:
+            # BASELINE config C5: an ensemble of independent unit cells batched into every launch (same programs, nb chains)
+            E = a.ensemble
+            ecells = [UnitCell.random(2, D, seed=100 + i) for i in range(E)]
+            emsgs = [msgs_list[0]] * E
+            for s in BLOCK_SIDES_CCW:
+                batch = [bp._side_inputs(c, m, comps[s]) for c, m in zip(ecells, emsgs)]
+                comps[s].load(engs[s], E)
+                engs[s].upload(0, comps[s].pack_inputs(batch))
+                engs[s].sync()
+            resident_step()
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            resident_step()
+            resident_step()
+            e1.record()
+            torch.cuda.synchronize()
+            ems = e0.elapsed_time(e1) / 2
+            line["ensemble"] = {"unit_cells_per_gpu": E, "ms_per_step": ems, "value": 6 * E / (ems * 1e-3), "unit": UNIT,
+                                "note": "independent unit cells as extra chains of the same launches (kernels take a chain index)"}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_sample(a, cells[0], msgs_list[0], a.cpu_budget_s)
         if world == 1 and a.ite_steps > 0:

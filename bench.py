@@ -177,6 +177,11 @@ def ite_metric(a, cell, messages, cfg, cpu_bp):
 def run_reference_arm(a, rank):
     if rank != 0:
         return
+    try:                      # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host thread back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     from kagomeperiodicbp_b200.containers import UnitCell
     from oracle import bp_np
     cell = UnitCell.random(2, a.D, seed=0)

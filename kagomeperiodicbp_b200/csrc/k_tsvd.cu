@@ -45,7 +45,7 @@ int tsvd_block(int64_t m, int64_t n, int64_t keep) {
 
 int64_t tsvd_work_elems(int64_t m, int64_t n) {
   const int64_t q = m < n ? n : m, b = TSVD_BMAX;
-  return 4 * rup8(q) * b + 16 * b * b + m * n + 64;
+  return 4 * rup8(q) * b + 17 * b * b + m * n + 64;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -65,17 +65,21 @@ __global__ void tsvd_randq_kernel(cplx* __restrict__ base, long long chain_strid
 }
 
 // ------------------------------------------------------------------------------------------------
-// One CTA per chain: Cholesky G = R^H R of a b x b Hermitian Gram matrix (given as `nsplit` partial sums) in
-// shared memory, then Rinv = R^{-1}.  Blocked by panels of 16: the diagonal block is factored and inverted by one
-// warp with warp-level synchronisation only, the panel rows and the trailing update are block-parallel (3 barriers
-// per panel instead of 3 per column), and the off-diagonal blocks of the inverse follow level by level.  R stays in
-// the upper triangle, R^{-1} is built transposed in the strict lower triangle, its diagonal in dinv.
-// Columns whose pivot is below TSVD_PIVOT_DEAD of their diagonal are dropped (row of R, column of Rinv = 0: the
-// orthonormalised block gets a zero column there).  stat[chain] = min over live columns of pivot/diagonal.
+// One CTA per chain: Cholesky G = R^H R of a b x b Hermitian Gram matrix (given as `nsplit` partial sums) in shared
+// memory, blocked by panels of 16:
+//   A  the diagonal block is factored by 8 warps, one thread per entry kept in a register; the pivot row / column of each
+//      of the 16 dependent steps goes through a double-buffered shared-memory line and ONE 256-thread named barrier
+//      (a single warp doing this alone is ~5x slower: nothing hides its dependent-issue latency);
+//   B  the panel rows by forward substitution, one thread per column, the column in registers;
+//   C  the trailing update, block-parallel.
+// R^{-1} is never formed: the orthonormalised block Y R^{-1} is a triangular solve per row (trsm_kernel), which is both
+// cheaper than inverting in one CTA and more accurate.  Columns whose pivot is below TSVD_PIVOT_DEAD of their diagonal are
+// dropped (row of R = 0, dinv = 0: the orthonormalised block gets a zero column there).  stat[chain] = min over live
+// columns of pivot/diagonal.  Outputs: R (b x b, upper, row-major), Dinv (b entries, 1/R_jj in .x).
 constexpr int CNB = 16;
 
-__global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit,
-                                                        long long R_, long long Rinv_, int b, double* __restrict__ stat) {
+__global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
+                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat) {
   extern __shared__ __align__(16) unsigned char ch_raw[];
   const int ld = b + 1;                                            // odd row stride: the 16 rows of a panel fall into different banks
   cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x ld
@@ -96,21 +100,9 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
   if (t == 0) sh_min = 1.0;
   __syncthreads();
 
-#ifdef KBP_CHOL_TIMING
-  long long tA = 0, tB = 0, tC = 0, tL = 0, tF = 0, t_start = clock64(), tt0;
-#define TICK() tt0 = clock64()
-#define TOCK(acc) acc += clock64() - tt0
-#else
-#define TICK()
-#define TOCK(acc)
-#endif
   for (int p0 = 0; p0 < b; p0 += CNB) {
     const int p1 = p0 + CNB < b ? p0 + CNB : b, pw = p1 - p0;
-    TICK();
-    // ---- phase A (8 warps, one thread per entry of the 16 x 16 diagonal block, entry kept in a register): 16 pivot steps,
-    //      the pivot row / column published through a double-buffered 2 x 16 shared-memory line and ONE 256-thread named
-    //      barrier per step; then the inverse of the block, 15 steps of (term per thread, half-warp shuffle sum).  A single
-    //      warp doing this alone is ~5x slower: nothing hides its dependent-issue latency.
+    // ---- phase A
     if (t < 256) {
       const int row = t >> 4, col = t & 15;
       const bool in = row < pw && col < pw;
@@ -144,53 +136,31 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
       }
       if (t == 0) sh_min = fmin(sh_min, mn);
       if (in && col >= row) S[(p0 + row) * ld + p0 + col] = v;       // R (upper)
-      asm volatile("bar.sync 1, 256;");
-      // inverse X = R^{-1} of the block: thread (l = t >> 4, r = t & 15) holds x_rl;  x_il = -dinv_i sum_{r = i+1..l} R[i][r] x_rl
-      {
-        const int l = t >> 4, rr = t & 15;
-        const bool act = l < pw && rr < pw;
-        cplx x = (act && rr == l) ? cmake(dinv[p0 + l], 0.0) : cmake(0.0, 0.0);
-        for (int i = CNB - 2; i >= 0; --i) {
-          cplx term = cmake(0.0, 0.0);
-          if (act && i < pw && rr > i && rr <= l) term = cmul(S[(p0 + i) * ld + p0 + rr], x);
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) {
-            term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
-            term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
-          }
-          if (act && rr == i && i < l) x = cscale(term, -dinv[p0 + i]);
-        }
-        if (act && rr < l) S[(p0 + l) * ld + p0 + rr] = x;             // X[rr][l] parked at S[l][rr]
-      }
     }
     __syncthreads();
-    TOCK(tA);
     const int rem = b - p1;
     if (rem > 0) {
-      TICK();
-      // ---- phase B: panel rows  R[r][l] = sum_{r' <= r} conj(X[r'][r]) S[r'][l],  l >= p1  (registers, then write)
-      cplx outv[2];
-      const int nel = pw * rem;
+      // ---- phase B: R[r][l] = (S[r][l] - sum_{r' < r} conj(R[r'][r]) R[r'][l]) / R[r][r],  l >= p1
+      if (t < rem) {
+        const int l = p1 + t;
+        cplx colv[CNB];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int e = t + u * 1024;
-        outv[u] = cmake(0.0, 0.0);
-        if (e < nel) {
-          const int r = p0 + e / rem, l = p1 + e % rem;
-          cplx acc = cscale(S[r * ld + l], dinv[r]);
-          for (int rp = p0; rp < r; ++rp) acc = cadd(acc, ccmul(S[r * ld + rp], S[rp * ld + l]));
-          outv[u] = acc;
+        for (int r = 0; r < CNB; ++r) {
+          cplx acc = cmake(0.0, 0.0);
+          if (r < pw) {
+            acc = S[(p0 + r) * ld + l];
+#pragma unroll
+            for (int rp = 0; rp < r; ++rp) {
+              const cplx v = ccmul(S[(p0 + rp) * ld + p0 + r], colv[rp]);
+              acc.x -= v.x; acc.y -= v.y;
+            }
+            acc = cscale(acc, dinv[p0 + r]);
+            S[(p0 + r) * ld + l] = acc;
+          }
+          colv[r] = acc;
         }
       }
       __syncthreads();
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int e = t + u * 1024;
-        if (e < nel) S[(p0 + e / rem) * ld + p1 + e % rem] = outv[u];
-      }
-      __syncthreads();
-      TOCK(tB);
-      TICK();
       // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
       for (int e = t; e < rem * rem; e += nt) {
         const int i = p1 + e / rem, l = p1 + e % rem;
@@ -205,78 +175,84 @@ __global__ void __launch_bounds__(1024) chol_inv_kernel(cplx* __restrict__ base,
         }
       }
       __syncthreads();
-      TOCK(tC);
     }
   }
-  TICK();
-  if (R_ >= 0) {
-    cplx* R = cb + R_;
-    for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[(e / b) * ld + e % b] : cmake(0.0, 0.0);
-  }
-  __syncthreads();
-  // ---- off-diagonal blocks of the inverse, level d = block column - block row:
-  //      X_pq = -X_pp (sum_{p < r <= q} R_pr X_rq);   X[j][l] (j < l) lives at S[l][j], X[l][l] = dinv[l]
+  cplx* R = cb + R_;
+  for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[(e / b) * ld + e % b] : cmake(0.0, 0.0);
+  cplx* Dv = cb + Dinv_;
+  for (int i = t; i < b; i += nt) Dv[i] = cmake(dinv[i], 0.0);
+  // inverses of the 16 x 16 diagonal blocks (what the blocked triangular solve multiplies by), all panels in parallel, off
+  // the factorisation's critical path: 256 threads per panel, thread (l, r) holds x_rl, x_il = -dinv_i sum_{r=i+1..l} R[i][r] x_rl
+  // reduced over the 16 lanes of a half warp -- no block barrier
+  cplx* Xd = cb + Xd_;
   const int nblk = (b + CNB - 1) / CNB;
-  for (int d = 1; d < nblk; ++d) {
-    const int nel = (nblk - d) * CNB * CNB;
-    cplx tv[2];
+  for (int pb = t >> 8; pb < nblk; pb += nt >> 8) {
+    const int p0 = pb * CNB, pw = (p0 + CNB < b ? CNB : b - p0);
+    const int l = (t >> 4) & 15, rr = t & 15;
+    const bool act = l < pw && rr < pw;
+    cplx x = (act && rr == l) ? cmake(dinv[p0 + l], 0.0) : cmake(0.0, 0.0);
+    for (int i = CNB - 2; i >= 0; --i) {
+      cplx term = cmake(0.0, 0.0);
+      if (act && i < pw && rr > i && rr <= l) term = cmul(S[(p0 + i) * ld + p0 + rr], x);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + u * 1024;
-      tv[u] = cmake(0.0, 0.0);
-      if (e < nel) {
-        const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) {
-          cplx acc = cscale(S[ip * ld + l], dinv[l]);               // j == l
-          for (int j = (pb + 1) * CNB; j < l; ++j) acc = cfma(S[ip * ld + j], S[l * ld + j], acc);
-          tv[u] = acc;
-        }
+      for (int o = 8; o > 0; o >>= 1) {
+        term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
+        term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
       }
+      if (act && rr == i && i < l) x = cscale(term, -dinv[p0 + i]);
     }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + u * 1024;
-      if (e < nel) {
-        const int pb = e / (CNB * CNB), ip = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) S[l * ld + ip] = tv[u];                           // T, parked where X_pq will go
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + u * 1024;
-      tv[u] = cmake(0.0, 0.0);
-      if (e < nel) {
-        const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) {
-          cplx acc = cscale(S[l * ld + i], dinv[i]);                 // i' == i
-          for (int ip = i + 1; ip < (pb + 1) * CNB; ++ip) acc = cfma(S[ip * ld + i], S[l * ld + ip], acc);
-          tv[u] = cmake(-acc.x, -acc.y);
-        }
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = t + u * 1024;
-      if (e < nel) {
-        const int pb = e / (CNB * CNB), i = pb * CNB + (e % (CNB * CNB)) / CNB, l = (pb + d) * CNB + e % CNB;
-        if (l < b) S[l * ld + i] = tv[u];
-      }
-    }
-    __syncthreads();
-  }
-  cplx* Rinv = cb + Rinv_;
-  for (int e = t; e < b * b; e += nt) {
-    const int i = e / b, l = e % b;
-    Rinv[e] = i < l ? S[l * ld + i] : (i == l ? cmake(dinv[i], 0.0) : cmake(0.0, 0.0));
+    Xd[pb * CNB * CNB + rr * CNB + l] = (act && rr <= l) ? x : cmake(0.0, 0.0);     // X[rr][l]
   }
   if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], sh_min);
-#ifdef KBP_CHOL_TIMING
-  TOCK(tL);
-  if (t == 0) printf("[chol b=%d] total %lld  A %lld (factor %lld)  B %lld  C %lld  levels+io %lld cycles\n", b, clock64() - t_start, tA, tF, tB, tC, tL);
-#endif
+}
+
+// Out (rows x b) = Y R^{-1} for upper-triangular R by block forward substitution over the 16-column panels:
+//     x_p = (y_p - sum_{r < p} x_r R_{r,p}) X_pp,        X_pp = inverse of the diagonal block (from chol_kernel).
+// One CTA per 32 rows, thread (row, c): the 16 threads of a row sit in one half warp, so the panel loop needs warp-level
+// synchronisation only.  R and the X_pp live in shared memory.
+__global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
+                                                   long long Out_, int rows, int b) {
+  extern __shared__ __align__(16) unsigned char tr_raw[];
+  const int nblk = (b + CNB - 1) / CNB;
+  cplx* Rs = reinterpret_cast<cplx*>(tr_raw);                     // b x b (row-major, upper)
+  cplx* Xs = Rs + (size_t)b * b;                                  // nblk x 16 x 16
+  cplx* xs = Xs + (size_t)nblk * CNB * CNB;                       // 32 x (b + 1): solved entries of the CTA's rows
+  cplx* tmp = xs + 32 * (size_t)(b + 1);                          // 32 x 17
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const cplx* R = cb + R_;
+  const cplx* Xd = cb + Xd_;
+  const int t = threadIdx.x;
+  for (int e = t; e < b * b; e += blockDim.x) Rs[e] = R[e];
+  for (int e = t; e < nblk * CNB * CNB; e += blockDim.x) Xs[e] = Xd[e];
+  __syncthreads();
+  const int r = t >> 4, c = t & 15;
+  const int row = blockIdx.x * 32 + r;
+  const bool ok = row < rows;
+  const cplx* y = cb + Y_ + (long long)row * b;
+  cplx* out = cb + Out_ + (long long)row * b;
+  cplx* xr = xs + r * (b + 1);
+  cplx* tr = tmp + r * 17;
+  for (int pb = 0; pb < nblk; ++pb) {
+    const int p0 = pb * CNB, col = p0 + c;
+    cplx acc = (ok && col < b) ? y[col] : cmake(0.0, 0.0);
+    if (col < b)
+      for (int i = 0; i < p0; ++i) {
+        const cplx v = cmul(xr[i], Rs[i * b + col]);
+        acc.x -= v.x; acc.y -= v.y;
+      }
+    tr[c] = acc;
+    __syncwarp();
+    cplx x = cmake(0.0, 0.0);
+    const cplx* X = Xs + pb * CNB * CNB;
+#pragma unroll
+    for (int cp = 0; cp < CNB; ++cp)
+      if (cp <= c) x = cfma(tr[cp], X[cp * CNB + c], x);
+    if (col < b) {
+      xr[col] = x;
+      if (ok) out[col] = x;
+    }
+    __syncwarp();
+  }
 }
 
 // How far span(Vh) is from an invariant subspace of A^H A, and the discarded weight, in two launches.
@@ -392,26 +368,21 @@ __global__ void __launch_bounds__(1024) phase_fix_kernel(cplx* __restrict__ base
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int k = w; k < keep; k += nw) {
     cplx* row = Vh + (long long)k * n;
-    double best = -1.0;
-    int bi = 0;
+    // phase reference: <r, row> real positive for a fixed pseudo-random vector r (continuous in the row, unlike "largest entry")
+    cplx acc = cmake(0.0, 0.0);
     for (int c = lane; c < n; c += 32) {
-      const double v = cabs2(row[c]);
-      if (v > best) { best = v; bi = c; }
+      const unsigned long long h = splitmix(0x51ed27ull + (unsigned long long)c), h2 = splitmix(h);
+      const cplx r = cmake((double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5, (double)(h2 >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+      acc = cadd(acc, ccmul(r, row[c]));
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
+    acc = warp_sum(acc);
+    const double best = cabs2(acc);
     if (!(best > 0.0)) continue;
-    const cplx p = row[bi];
     const double inv = rsqrt(best);
-    const cplx ph = cmake(p.x * inv, p.y * inv);            // unit phase of the pivot entry
+    const cplx ph = cmake(acc.x * inv, acc.y * inv);
     __syncwarp();
     for (int c = lane; c < n; c += 32) {
-      cplx v = cmulc(row[c], ph);                           // * conj(ph)
-      if (c == bi) v.y = 0.0;
-      row[c] = v;
+      row[c] = cmulc(row[c], ph);                           // * conj(ph)
     }
     if (us_too)
       for (int r = lane; r < m; r += 32) US[(long long)r * keep + k] = cmul(US[(long long)r * keep + k], ph);
@@ -436,13 +407,19 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
 // row ranges (more CTAs on a product whose output is only b x b) which the Cholesky kernel adds up.
 constexpr int GRAM_SPLIT = 4;
 
-static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Rinv, int64_t R_out, int64_t rows, int b, double* stat) {
+static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat) {
   const int split = rows >= 256 ? GRAM_SPLIT : 1;
   gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
   const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 2 * sizeof(double) * (size_t)b + 32;
-  chol_inv_kernel<<<a.nb, 1024, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Rinv, b, stat);
+  const int64_t Xd = Dinv + b;                                     // diagonal-block inverses behind the 1/diagonal entries
+  chol_kernel<<<a.nb, 1024, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat);
   ++*a.launches;
-  if (T >= 0) gemm(a, T, Y, Rinv, rows, b, b, OP_N, OP_N);      // T < 0: only R is wanted
+  if (T >= 0) {                                                   // T < 0: only R is wanted
+    const int nblk = (b + CNB - 1) / CNB;
+    const size_t smem2 = sizeof(double2) * ((size_t)b * b + (size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17) + 32;
+    trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b);
+    ++*a.launches;
+  }
   return T;
 }
 
@@ -459,7 +436,8 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
                           int nr_bulk, int slot_lognorm, int slot_trunc, int b, int64_t warm) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+    cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     attr_set = true;
   }
   static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
@@ -479,7 +457,8 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
   int64_t buf[4];                     // four q x b panels: Q, W, scratch, check product
   for (int i = 0; i < 4; ++i) { buf[i] = o; o += qp * b; }
   const int64_t Gp = o; o += GRAM_SPLIT * bb;
-  const int64_t Ri = o; o += bb;
+  const int64_t Ri = o; o += bb;      // 1 / diagonal of the last Cholesky factor (b entries)
+  const int64_t Rs = o; o += bb;      // the last Cholesky factor when the caller does not keep it
   const int64_t R1 = o; o += bb;
   const int64_t R2 = o; o += bb;
   const int64_t Rm = o; o += bb;
@@ -529,14 +508,14 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     for (; done < target; ++done) {
       gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
       if (!ordered) {
-        cholqr_pass(a, f0, f1, Gp, Ri, -1, m, b, stat);               // Y = orth(W)      -> f1
+        cholqr_pass(a, f0, f1, Gp, Ri, Rs, m, b, stat);               // Y = orth(W)      -> f1
         gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                      // Z = A^H Y        -> f0
-        cholqr_pass(a, f0, f1, Gp, Ri, -1, n, b, stat);               // orth(Z)          -> f1
-        if (done + 1 == target) { cholqr_pass(a, f1, f0, Gp, Ri, -1, n, b, stat); replace_q(f0); }   // twice on the last one
+        cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f1
+        if (done + 1 == target) { cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat); replace_q(f0); }   // twice on the last one
         else replace_q(f1);
       } else {
         gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
-        cholqr_pass(a, f1, f0, Gp, Ri, -1, n, b, stat);               // Q = orth(Z)      -> f0
+        cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // Q = orth(Z)      -> f0
         replace_q(f0);
       }
     }

@@ -94,3 +94,22 @@ def test_full_ite_step_matches_oracle():
     # the untouched tensor is unchanged
     c = ({0, 1, 2} - {a, b}).pop()
     assert np.array_equal(new_cell.tensors()[c], cell.tensors()[c])
+
+
+def test_ite_descends_into_the_known_energy_band():
+    """known-answer sanity: full-update ITE of a random D=2 unit cell of the Kagome Heisenberg AFM must bring
+    the energy per site below the simple-update value region and never below the best variational D=2 energy
+    (reference: scripts/plot/afmh_benchmarking.py:34-42, data/unit_cells/best/D=2 energy=-0.4046...)."""
+    from kagomeperiodicbp_b200 import edge_env, ite_flow
+    from kagomeperiodicbp_b200.containers import BPConfig, UnitCell
+    D, N, chi = 2, 2, 18
+    cfg = BPConfig(trunc_dim=8, msg_diff_terminate=1e-6, msg_diff_good_enough=1e-5, damping=0.1, init_msg="UQ", max_iterations=50)
+    cell, msgs = UnitCell.random(2, D, seed=0), None
+    energies = []
+    for dt, sweeps in ((0.1, 3), (0.05, 2)):
+        for _ in range(sweeps):
+            for mode in edge_env.MODES:
+                cell, msgs, _, _ = ite_flow.ite_per_mode(cell, msgs, N, mode, [(e, dt) for e in edge_env.EDGES], cfg, chi)
+            energies.append(ite_flow.measure_energies(cell, msgs, N, chi, mode="A").mean_energy)
+    assert energies[-1] < energies[0]
+    assert -0.4047 < energies[-1] < -0.375, energies

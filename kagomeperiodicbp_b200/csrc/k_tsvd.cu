@@ -209,20 +209,18 @@ __global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, lon
 // Out (rows x b) = Y R^{-1} for upper-triangular R by block forward substitution over the 16-column panels:
 //     x_p = (y_p - sum_{r < p} x_r R_{r,p}) X_pp,        X_pp = inverse of the diagonal block (from chol_kernel).
 // One CTA per 32 rows, thread (row, c): the 16 threads of a row sit in one half warp, so the panel loop needs warp-level
-// synchronisation only.  R and the X_pp live in shared memory.
+// synchronisation only.  The X_pp and the solved entries live in shared memory, R is read through L2.
 __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
                                                    long long Out_, int rows, int b) {
   extern __shared__ __align__(16) unsigned char tr_raw[];
   const int nblk = (b + CNB - 1) / CNB;
-  cplx* Rs = reinterpret_cast<cplx*>(tr_raw);                     // b x b (row-major, upper)
-  cplx* Xs = Rs + (size_t)b * b;                                  // nblk x 16 x 16
+  cplx* Xs = reinterpret_cast<cplx*>(tr_raw);                     // nblk x 16 x 16
   cplx* xs = Xs + (size_t)nblk * CNB * CNB;                       // 32 x (b + 1): solved entries of the CTA's rows
   cplx* tmp = xs + 32 * (size_t)(b + 1);                          // 32 x 17
   cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* R = cb + R_;
   const cplx* Xd = cb + Xd_;
   const int t = threadIdx.x;
-  for (int e = t; e < b * b; e += blockDim.x) Rs[e] = R[e];
   for (int e = t; e < nblk * CNB * CNB; e += blockDim.x) Xs[e] = Xd[e];
   __syncthreads();
   const int r = t >> 4, c = t & 15;
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long
     cplx acc = (ok && col < b) ? y[col] : cmake(0.0, 0.0);
     if (col < b)
       for (int i = 0; i < p0; ++i) {
-        const cplx v = cmul(xr[i], Rs[i * b + col]);
+        const cplx v = cmul(xr[i], __ldg(R + i * b + col));       // R (b x b) stays in L2: 16 consecutive columns per row of threads
         acc.x -= v.x; acc.y -= v.y;
       }
     tr[c] = acc;
@@ -416,7 +414,7 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
   ++*a.launches;
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
-    const size_t smem2 = sizeof(double2) * ((size_t)b * b + (size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17) + 32;
+    const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17) + 32;
     trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b);
     ++*a.launches;
   }

@@ -181,3 +181,20 @@ def test_normalize_embed_eye(eng):
     ref[3:, :, 5:] = (-0.1 + 0.2j) * b
     assert np.allclose(s, ref, atol=1e-15)
     assert np.array_equal(e, np.eye(6))
+
+
+def test_svd_subspace_widest_block(eng):
+    """keep = 42 (chi = 2 D^2 + 10 at D = 4: the ToCore / ToEdge chains) runs the subspace path with the widest block the
+    b x b kernels take (112): their shared-memory footprints must fit."""
+    m, n, keep = 672, 672, 42
+    a = rnd(m, n)
+    u, s, vh = np.linalg.svd(a, full_matrices=False)
+    s = np.exp(-0.07 * np.arange(len(s)))
+    a = (u * s) @ vh
+    before = eng.svd_counters()
+    res, sl = run(eng, lambda p, t: list(p.svd_trunc(t[0], keep, True, 0, 1)), [[a]])
+    after = eng.svd_counters()
+    assert after["subspace"] == before["subspace"] + 1
+    us, v = res[0]
+    ref = (u[:, :keep] * s[:keep]) @ vh[:keep]
+    assert np.linalg.norm(us @ v * np.linalg.norm(s) - ref) <= 1e-11 * np.linalg.norm(s)

@@ -497,7 +497,7 @@ static int svd_truncate_jacobi(const Arena& a, int64_t A, int64_t US, int64_t Vh
       ++*a.launches;
     }
     cudaMemcpyAsync(a.svd_off_host, cur, sizeof(double) * a.nb, cudaMemcpyDeviceToHost, a.stream);
-    if (cudaStreamSynchronize(a.stream) != cudaSuccess) return -1;
+    if (stream_wait(a) != cudaSuccess) return -1;
     ++sweeps;
     if (debug) {
       fprintf(stderr, "[kbp svd %lldx%lld] sweep %d off:", (long long)m, (long long)n, s);

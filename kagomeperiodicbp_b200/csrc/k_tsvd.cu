@@ -542,7 +542,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     *a.launches += 2;
     // one host round trip: [stat | resid | ratio | discfrac] are contiguous in svd_off
     cudaMemcpyAsync(a.svd_off_host, a.svd_off, sizeof(double) * 4 * a.nb, cudaMemcpyDeviceToHost, a.stream);
-    if (cudaStreamSynchronize(a.stream) != cudaSuccess) return -1;
+    if (stream_wait(a) != cudaSuccess) return -1;
     double worst = 0.0, minpiv = 1.0, minratio = 1.0, maxdisc = 0.0;
     for (int c = 0; c < a.nb; ++c) {
       const double pv = a.svd_off_host[c], rs = a.svd_off_host[a.nb + c], ra = a.svd_off_host[2 * a.nb + c], df = a.svd_off_host[3 * a.nb + c];

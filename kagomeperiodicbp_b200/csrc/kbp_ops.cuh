@@ -17,6 +17,7 @@ struct Arena {
   int n_slots;
   int nb;
   cudaStream_t stream;
+  cudaEvent_t block_event;  // non-null: host waits block on this event (yield the core) instead of spinning in cudaStreamSynchronize
   double2* scratch;       // split-K partial tiles: [nb][scratch_stride] complex128 (may be null)
   int64_t scratch_stride;
   int* counters_dev;      // split-K tile semaphores: [nb][4096] ints, zero between launches
@@ -28,6 +29,15 @@ struct Arena {
                           // ratio, discarded fraction, norms, partial sums of the check kernels)
   double* svd_off_host;   // pinned host mirror: [4][nb]
 };
+
+// host wait for everything queued on the arena's stream.  With several ranks x six launch threads per node the default
+// spin-wait oversubscribes the host cores; a blocking event wait costs a few tens of microseconds once or twice per SVD.
+inline cudaError_t stream_wait(const Arena& a) {
+  if (!a.block_event) return cudaStreamSynchronize(a.stream);
+  cudaError_t e = cudaEventRecord(a.block_event, a.stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(a.block_event);
+}
 
 enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };   // as-is, transpose, conj-transpose, conj
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
   // the pair counts as unconverged iff |c|^2 > tol^2 a b (no division / square root on the decision path); the rotation
   // needs three dependent special-function evaluations: rsqrt(|c|^2) || rsqrt(d^2 + 4|c|^2), a reciprocal, rsqrt(1 + t^2)
   if (!(r2 > (SMALL_TOL * SMALL_TOL) * a * b)) return;
-  my_off = 1.0;
+  my_off = fmax(my_off, r2 * __drcp_rn(a * b));        // cos^2 of the pair's angle (off the rotation's critical path)
   const double inv = rsqrt(r2), ab = r2 * inv;
   const double er = cr * inv, ei = ci * inv;
   const double d = a - b;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
           const double r2 = fma(cr, cr, ci * ci);
           if (a > floor2 && b > floor2 && r2 > 0.0) {
             if (r2 > (SMALL_TOL * SMALL_TOL) * a * b) {
-              my_off = 1.0;
+              my_off = fmax(my_off, r2 * __drcp_rn(a * b));
               // x_j' = e x_j with e = c/|c| makes <x_i, x_j'> = |c| real; then a real rotation by theta,
               // tan(2 theta) = 2|c| / (a - b), small-angle root
               const double inv = rsqrt(r2), ab = r2 * inv;
@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
       if (lane == 0) sh_flag = x;
     }
     __syncthreads();
-    converged = sh_flag <= SMALL_TOL;      // (my_off is 1 for a lane group that rotated in this sweep, else 0)
+    // my_off = largest cos^2 rotated away in this sweep (0: nothing was above tol).  One-sided Jacobi converges quadratically
+    // at the end: once every pair of a sweep started below sqrt(tol), the next sweep would find nothing to do -- skip it
+    converged = sh_flag <= SMALL_TOL;
 #ifdef KBP_SMALL_DEBUG
     if (t == 0) printf("[small %dx%d] sweep %d max off %.3e  cycles %lld\n", p, q, sweep, sh_flag, clock64() - tstart);
 #endif

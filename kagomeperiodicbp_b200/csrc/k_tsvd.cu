@@ -497,8 +497,18 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     if (nq == f0) f0 = old; else if (nq == f1) f1 = old; else f2 = old;
     if (old == warm) { if (f0 == warm) f0 = buf[0]; else if (f1 == warm) f1 = buf[0]; else if (f2 == warm) f2 = buf[0]; }
   };
-  int done = 0, target = ordered ? it_warm : it_cold;
+  // per-op schedule: the same truncation of the same program (next BP iteration: nearly the same spectrum) remembers after
+  // how many iterations its check passed -- first check there next time instead of at the fixed default
+  static const bool adaptive = getenv("KBP_TSVD_ADAPT") && atoi(getenv("KBP_TSVD_ADAPT")) != 0;   // opt-in: measured neutral
+  const long long sched_key = (long long)A * 4096 + (m % 64) * 64 + (n % 64);
+  int first = ordered ? it_warm : it_cold;
+  if (adaptive && !ordered) {
+    auto it = a.sched->find(sched_key);
+    if (it != a.sched->end()) first = it->second;
+  }
+  int done = 0, target = first;
   if (target < 1) target = 1;
+  int checks = 0;
   while (true) {
     tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
     ++*a.launches;
@@ -558,7 +568,17 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     // path.  A fast round whose Cholesky pivots were small says nothing either way: it is redone with safe iterations.
     const bool trusted = !rr_ordered || minpiv >= TSVD_PIVOT_TRUST;
     const bool collapse = trusted && minratio < TSVD_MIN_RATIO && maxdisc > 1e-24;
-    if (!collapse && trusted && worst <= TSVD_RES_TOL) break;
+    ++checks;
+    if (!collapse && trusted && worst <= TSVD_RES_TOL) {
+      if (adaptive && !is_warm) {
+        // passed at the first check with a residual far below the tolerance: try one iteration less next time; needed
+        // more checks: go straight to this count next time
+        int next = done;
+        if (checks == 1 && worst <= TSVD_RES_TOL * 0.03 && done > 3) next = done - 1;
+        (*a.sched)[sched_key] = next;
+      }
+      break;
+    }
     if (collapse || done >= it_max) {
       if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld] FALLBACK after %d iterations: resid %.3e s_k/s_1 %.3e\n", (long long)m, (long long)n, done, worst, minratio);
       if (warm >= 0) a.warm->erase((long long)warm);

@@ -23,6 +23,7 @@ struct Arena {
   int* counters_dev;      // split-K tile semaphores: [nb][4096] ints, zero between launches
   int64_t* launches;      // host counter of kernel launches
   int64_t* counters;      // host counters [8]: see svd_truncate
+  std::unordered_map<long long, int>* sched;  // per-truncation iteration schedule learned from the previous run of the same program
   std::unordered_map<long long, int>* warm;   // warm-start buffers that hold a valid Ritz basis: offset -> block size
   // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
   double* svd_off;        // device: [6 + 32*160][nb]  (Jacobi: off current / previous sweep, ||A||_F^2; subspace: pivot, residual,

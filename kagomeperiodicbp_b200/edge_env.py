@@ -89,9 +89,13 @@ def core_site_indices(N: int):
     return idx
 
 
-def core_env_tensors(B, N: int, mps_bottom_up, mps_top_down):
-    """zip the two ToCore boundary MPSs (direction U / D) outside the core and return the 12 ring tensors m0..m11
-    (kagome_to_core.py:192-257 with bottom-up direction U).  Inputs: lists of site arrays [Dl, D^2, Dr]."""
+CORE_DIRECTIONS = {"U": ("U", "D", 0), "DL": ("DL", "UR", 4), "DR": ("DR", "UL", 8)}   # bottom-up side, top-down side, ring rotation
+
+
+def core_env_tensors(B, N: int, mps_bottom_up, mps_top_down, direction: str = "U"):
+    """zip the two ToCore boundary MPSs (bottom-up ``direction`` / its opposite) outside the core and return the 12 ring
+    tensors m0..m11 (kagome_to_core.py:192-257; the ring is rotated by 0 / 4 / 8 places for U / DL / DR, :245-255).
+    Inputs: lists of site arrays [Dl, D^2, Dr]."""
     s = 2 * N - 3
     bu, td = [np.asarray(a) for a in mps_bottom_up], [np.asarray(a) for a in mps_top_down]
     assert len(bu) == 5 + 2 * s and len(td) == 7 + 2 * s, (len(bu), len(td))
@@ -111,7 +115,9 @@ def core_env_tensors(B, N: int, mps_bottom_up, mps_top_down):
         else:
             Rt = B.tensordot(B.tensordot(a, Rt, ([2], [0])), b, ([1, 2], [1, 2]))
     td[s] = B.tensordot(Rt, td[s], ([0], [0]))
-    return bu[s + 2:s + 5] + td[s:s + 7] + bu[s:s + 2]
+    ring = bu[s + 2:s + 5] + td[s:s + 7] + bu[s:s + 2]
+    k = CORE_DIRECTIONS[direction][2]
+    return ring[-k:] + ring[:-k] if k else ring
 
 
 def core_network(B, N: int, cell, env12):

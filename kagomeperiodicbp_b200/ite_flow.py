@@ -7,8 +7,8 @@
 
 and the energy measurement ``measure_energies_and_observables_together`` (src/algo/measurements.py:163-243: six edge RDMs of
 one mode, energy per site = sum / 3).  Host code orchestrates and moves data; all tensor algebra runs through libkbp.so.
-The core is always reduced with bottom-up direction U (the reference draws it at random from {U, DL, DR},
-kagome_to_core.py:178-179; SURVEY 8d fixes U for reproducible runs).
+The core is reduced with bottom-up direction U unless told otherwise (the reference draws it at random from {U, DL, DR},
+kagome_to_core.py:178-179; SURVEY 8d fixes U for reproducible runs; `reduce_to_core(..., direction=)` takes all three).
 """
 from __future__ import annotations
 
@@ -41,13 +41,14 @@ def _device_bubblecon_fn(T_list, edges, angles, bubble_angle, order, chi, kets):
     return mp.A
 
 
-def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device: int = 0):
-    """the 12 ring tensors of the CoreTN (kagome_to_core.py:322-364): two truncated ToCore chains (directions U and D) run
-    concurrently on two streams, then the overlap zip on the device backend."""
+def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device: int = 0, direction: str = "U"):
+    """the 12 ring tensors of the CoreTN (kagome_to_core.py:322-364): two truncated ToCore chains (bottom-up ``direction`` in
+    {U, DL, DR} and its opposite) run concurrently on two streams, then the overlap zip on the device backend."""
+    bu_side, td_side, _ = edge_env.CORE_DIRECTIONS[direction]
     d, D = unit_cell.A.shape[0], unit_cell.A.shape[1]
     shapes = bp._msg_shapes(messages)
     futs = []
-    for side in ("U", "D"):
+    for side in (bu_side, td_side):
         comp = bp.compile_side_program(N, d, D, side, chi, shapes, None, depth="ToCore", epilogue=False)
         batch = [bp._side_inputs(unit_cell, messages, comp)]
         futs.append(bp._pool.submit(bp._run_side, side, comp, batch, device))
@@ -58,7 +59,7 @@ def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device
             raise bp.BubbleConError(f"non-finite values in the ToCore contraction towards {side}")
         o = outs[0]
         res[side] = [o[f"out{k}"] for k in range(len(o))]
-    return edge_env.core_env_tensors(backend(), N, res["U"], res["D"])
+    return edge_env.core_env_tensors(backend(), N, res[bu_side], res[td_side], direction)
 
 
 def edge_tn(unit_cell: UnitCell, env12, N: int, mode: str, edge: str, chi: int):

@@ -113,3 +113,21 @@ def test_ite_descends_into_the_known_energy_band():
             energies.append(ite_flow.measure_energies(cell, msgs, N, chi, mode="A").mean_energy)
     assert energies[-1] < energies[0]
     assert -0.4047 < energies[-1] < -0.375, energies
+
+
+@pytest.mark.parametrize("direction", ["DL", "DR"])
+def test_device_other_core_directions_match_reference(direction):
+    from kagomeperiodicbp_b200 import edge_env, ite, ite_flow
+    from kagomeperiodicbp_b200.containers import UnitCell
+    g = golden("ite_D2_N2.npz")
+    cell = UnitCell(g["A"], g["B"], g["C"])
+    msgs = device_messages(g, 2)
+    chi = int(g["chi"])
+    env12 = ite_flow.reduce_to_core(cell, msgs, 2, chi, direction=direction)
+    B = ite_flow.backend()
+    for e in edge_env.EDGES:
+        ti, tj, env, _ = ite_flow.edge_tn(cell, env12, 2, "A", e, chi)
+        rho = ite.rho_ij(B, ti, tj, env)
+        assert np.max(np.abs(rho - g[f"rdm_{direction}_A_{e}"])) < 1e-9, (direction, e)
+        energy = float(np.real(np.dot(rho.flatten(), g["h"].flatten())))
+        assert abs(energy - g[f"energy_{direction}_A_{e}"][0]) < 1e-8

@@ -121,6 +121,21 @@ def main():
                 print(f"  D={D} mode {mode.name} edge {key}: energy {energy.real:+.10f}  env bonds {[x.shape[0] for x in env]}"
                       f"{'  [ToEdge bubblecon]' if calls else ''}")
         ctn.bubblecon = orig_bubblecon
+        # the other two bottom-up directions the reference may draw (kagome_to_core.py:68, 178-179)
+        for dirn in (BlockSide.DL, BlockSide.DR):
+            core_d = reduce_full_kagome_to_core(tn, cfg.contraction, direction=dirn)
+            for n in core_d.nodes[9:]:
+                out[f"core_env_{dirn}_{n.name}"] = n.tensor
+            mode_tn = reduce_core_to_mode(core_d, UpdateMode.A)
+            for e in UpdateEdge.all_options():
+                et = reduce_mode_to_edge(mode_tn, e, cfg.contraction, arange_legs=False)
+                et.rearrange_tensors_and_legs_into_canonical_order()
+                t1, t2, env = et.edge_and_environment()
+                key = str(e).replace("(", "").replace(")", "").replace(", ", "").replace(" ", "")
+                rdm = rho_ij(t1, t2, mps_env=env)
+                out[f"rdm_{dirn}_A_{key}"] = rdm
+                out[f"energy_{dirn}_A_{key}"] = np.array([np.dot(rdm.flatten(), np.asarray(h).flatten()).real])
+            print(f"  D={D} direction {dirn}: done")
         np.savez_compressed(os.path.join(GOLD, f"ite_D{D}_N2.npz"), **out)
     with open(os.path.join(ROOT, "kagomeperiodicbp_b200", "core_tables.json"), "w") as f:
         json.dump(tables, f, indent=1)

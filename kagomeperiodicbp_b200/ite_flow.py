@@ -67,15 +67,42 @@ def edge_tn(unit_cell: UnitCell, env12, N: int, mode: str, edge: str, chi: int):
     return edge_env.edge_environment(backend(), N, unit_cell.tensors(), env12, mode, edge, chi, _device_bubblecon_fn)
 
 
+_PAULI = {"x": np.array([[0, 1], [1, 0]], dtype=np.complex128), "y": np.array([[0, -1j], [1j, 0]], dtype=np.complex128),
+          "z": np.array([[1, 0], [0, -1]], dtype=np.complex128)}
+
+
+def expectation_values_with_rdm(rdm) -> dict:
+    """(src/algo/measurements.py:522-545)  {pauli: (<sigma> on site i, <sigma> on site j)} from the one-site marginals of a
+    two-site RDM rho[i, i*, j, j*] -- 2 x 2 host arithmetic, as in the reference."""
+    rho_i = np.trace(rdm, axis1=2, axis2=3)
+    rho_j = np.trace(rdm, axis1=0, axis2=1)
+    return {k: (float(np.real(np.trace(s @ rho_i))), float(np.real(np.trace(s @ rho_j)))) for k, s in _PAULI.items()}
+
+
+def negativity_of_rdm(rdm) -> float:
+    """(src/algo/measurements.py:91-94, src/physics/metrics/_negativity.py:43-73)  sum of |negative eigenvalues| of the partial
+    transpose (first site) of the 4 x 4 two-site density matrix."""
+    pt = np.transpose(rdm, (1, 0, 2, 3))                               # i <-> i*
+    mat = np.transpose(pt, (0, 2, 1, 3)).reshape(4, 4)
+    w = np.linalg.eigvals(mat)
+    return float(sum(abs(x) for x in w if x.real < 0))
+
+
 @dataclass
 class MeasurementsOnUnitCell:
-    """(src/containers/results.py:8-20)"""
+    """(src/containers/results.py:8-30)"""
     energies: dict
     rdms: dict = field(default_factory=dict)
+    expectations: dict = field(default_factory=dict)      # {A|B|C: {x|y|z: mean over the edges the site appears on}}
+    entanglement: dict = field(default_factory=dict)      # negativity per edge
 
     @property
     def mean_energy(self) -> float:
         return sum(self.energies.values()) / 3
+
+    @property
+    def mean_expectation_values(self) -> dict:
+        return {k: sum(self.expectations[f][k] for f in "ABC") / 3 for k in "xyz"}
 
 
 def measure_energies(unit_cell: UnitCell, messages: dict, N: int, chi: int, h=None, mode: str = "A", env12=None) -> MeasurementsOnUnitCell:
@@ -84,13 +111,21 @@ def measure_energies(unit_cell: UnitCell, messages: dict, N: int, chi: int, h=No
     if env12 is None:
         env12 = reduce_to_core(unit_cell, messages, N, chi)
     B = backend()
-    energies, rdms = {}, {}
+    energies, rdms, ent = {}, {}, {}
+    acc = {f: {k: [0.0, 0] for k in "xyz"} for f in "ABC"}
     for e in edge_env.EDGES:
-        ti, tj, env, _ = edge_tn(unit_cell, env12, N, mode, e, chi)
+        ti, tj, env, info = edge_tn(unit_cell, env12, N, mode, e, chi)
         rho = ite.rho_ij(B, ti, tj, env)
         rdms[e] = rho
-        energies[f"({e[0]}, {e[1]})"] = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
-    return MeasurementsOnUnitCell(energies, rdms)
+        key = f"({e[0]}, {e[1]})"
+        energies[key] = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
+        ent[key] = negativity_of_rdm(rho)
+        for k, vals in expectation_values_with_rdm(rho).items():
+            for v, f in zip(vals, info["flavors"]):
+                acc[f][k][0] += v
+                acc[f][k][1] += 1
+    expectations = {f: {k: (acc[f][k][0] / acc[f][k][1] if acc[f][k][1] else 0.0) for k in "xyz"} for f in "ABC"}
+    return MeasurementsOnUnitCell(energies, rdms, expectations, ent)
 
 
 @dataclass

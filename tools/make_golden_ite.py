@@ -106,6 +106,11 @@ def main():
                 t1n, t2n, eig = apply_2local_gate(g=g, Dmax=D, Ti=t1, Tj=t2, mps_env=env)
                 t1n, t2n = t1n / np.linalg.norm(t1n), t2n / np.linalg.norm(t2n)
                 pair = np.tensordot(t1n, t2n, axes=([1], [1]))
+                if mode is UpdateMode.A:
+                    from algo.measurements import compute_negativity_of_rdm, expectation_values_with_rdm
+                    ev = expectation_values_with_rdm(rdm, force_real=True)
+                    out[f"expect_{key}"] = np.array([[ev[x][0], ev[x][1]] for x in ("x", "y", "z")], dtype=float)
+                    out[f"negativity_{key}"] = np.array([compute_negativity_of_rdm(rdm)], dtype=float)
                 out[f"rdm_{key}"] = rdm
                 out[f"energy_{key}"] = np.array([energy.real, energy.imag])
                 out[f"pair_{key}"] = pair

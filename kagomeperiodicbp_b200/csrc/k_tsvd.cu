@@ -480,15 +480,35 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     ordered = it != a.warm->end() && it->second == b;
   }
   const bool is_warm = ordered;
+  // The first round of a cold start (pseudo-random block, a fixed number of iterations, Rayleigh-Ritz, copy of the flags) is
+  // a constant launch sequence for a given op of a given program: captured into a CUDA graph on its second execution and
+  // replayed afterwards (~70 launches -> one).  Everything that depends on the flags stays on the plain path.
+  static const bool graphs_on = !(getenv("KBP_GRAPHS") && atoi(getenv("KBP_GRAPHS")) == 0);
+  TsvdGraph* tg = nullptr;
+  bool replayed = false, capturing = false;
+  if (graphs_on && !is_warm && !debug && a.tsvd_graphs) {
+    unsigned long long h = 1469598103934665603ull;
+    const long long keyv[10] = {(long long)A, (long long)US, (long long)Vh, (long long)work, (long long)m, (long long)n, (long long)keep,
+                                b, nr_bulk * 4096 + (slot_lognorm + 1) * 64 + (slot_trunc + 1), it_cold};
+    for (int i = 0; i < 10; ++i) { h ^= (unsigned long long)keyv[i]; h *= 1099511628211ull; }
+    if (a.tsvd_graphs->size() < 4096 || a.tsvd_graphs->count(h)) {
+      tg = &(*a.tsvd_graphs)[h];
+      if (tg->exec) replayed = true;
+      else if (!tg->bad && tg->seen++ >= 1) capturing = cudaStreamBeginCapture(a.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    }
+  }
+  const int64_t launches_before = *a.launches;
   if (ordered) {
     Qb = warm;                       // Ritz basis of the previous run of this op (n x b, orthonormal columns); read only
   } else {
     Qb = buf[0];
-    const long long total = (long long)n * b;
-    int gx = (int)((total + 255) / 256);
-    if (gx > 148 * 4) gx = 148 * 4;
-    tsvd_randq_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, Qb, total);
-    ++*a.launches;
+    if (!replayed) {
+      const long long total = (long long)n * b;
+      int gx = (int)((total + 255) / 256);
+      if (gx > 148 * 4) gx = 148 * 4;
+      tsvd_randq_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, Qb, total);
+      ++*a.launches;
+    }
   }
   // after `Qb = newbuf`, the old basis panel becomes free unless it is the persistent warm buffer
   auto replace_q = [&](int64_t nq) {
@@ -510,9 +530,14 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
   if (target < 1) target = 1;
   int checks = 0;
   while (true) {
+    const bool rr_ordered = ordered;
+    if (replayed && checks == 0) {
+      if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
+      Qb = tg->Qb; f0 = tg->f0; f1 = tg->f1; f2 = tg->f2; done = tg->done;
+      *a.launches += tg->launches;
+    } else {
     tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
     ++*a.launches;
-    const bool rr_ordered = ordered;
     for (; done < target; ++done) {
       gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
       if (!ordered) {
@@ -552,6 +577,19 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     *a.launches += 2;
     // one host round trip: [stat | resid | ratio | discfrac] are contiguous in svd_off
     cudaMemcpyAsync(a.svd_off_host, a.svd_off, sizeof(double) * 4 * a.nb, cudaMemcpyDeviceToHost, a.stream);
+    if (capturing && checks == 0) {
+      cudaGraph_t graph = nullptr;
+      const cudaError_t e1 = cudaStreamEndCapture(a.stream, &graph);
+      cudaError_t e2 = cudaErrorUnknown;
+      if (e1 == cudaSuccess && graph) e2 = cudaGraphInstantiate(&tg->exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e2 != cudaSuccess) { tg->exec = nullptr; tg->bad = true; cudaGetLastError(); return -1; }
+      tg->Qb = Qb; tg->f0 = f0; tg->f1 = f1; tg->f2 = f2; tg->done = done;
+      tg->launches = *a.launches - launches_before;
+      if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
+      capturing = false;
+    }
+    }
     if (stream_wait(a) != cudaSuccess) return -1;
     double worst = 0.0, minpiv = 1.0, minratio = 1.0, maxdisc = 0.0;
     for (int c = 0; c < a.nb; ++c) {

@@ -31,6 +31,7 @@ struct kbp_ctx {
   int64_t counters[8] = {0};
   std::unordered_map<long long, int> warm;
   std::unordered_map<long long, int> sched;
+  std::unordered_map<unsigned long long, kbp::TsvdGraph> tsvd_graphs;
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; bool bad = false; };
   std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of sync-free programs, keyed by a hash of the op stream
   int64_t graph_replays = 0;
@@ -97,6 +98,9 @@ static void drop_graphs(kbp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   c->graphs.clear();
+  for (auto& kv : c->tsvd_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  c->tsvd_graphs.clear();
 }
 
 static void free_arena(kbp_ctx* c) {
@@ -368,7 +372,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
-  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.sched = &c->sched; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.sched = &c->sched; a.tsvd_graphs = &c->tsvd_graphs; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
   a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };

@@ -10,6 +10,15 @@
 
 namespace kbp {
 
+// captured first round (random start, fixed number of iterations, Rayleigh-Ritz, flag copy) of one subspace-iteration SVD op
+struct TsvdGraph {
+  cudaGraphExec_t exec = nullptr;
+  long long Qb = 0, f0 = 0, f1 = 0, f2 = 0;
+  int done = 0, seen = 0;
+  long long launches = 0;
+  bool bad = false;
+};
+
 struct Arena {
   double2* base;          // nb * chain_stride complex128 elements
   int64_t chain_stride;   // elements per chain
@@ -24,6 +33,7 @@ struct Arena {
   int64_t* launches;      // host counter of kernel launches
   int64_t* counters;      // host counters [8]: see svd_truncate
   std::unordered_map<long long, int>* sched;  // per-truncation iteration schedule learned from the previous run of the same program
+  std::unordered_map<unsigned long long, TsvdGraph>* tsvd_graphs;   // per-op CUDA graphs of the first round (cleared with the arena)
   std::unordered_map<long long, int>* warm;   // warm-start buffers that hold a valid Ritz basis: offset -> block size
   // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
   double* svd_off;        // device: [6 + 32*160][nb]  (Jacobi: off current / previous sweep, ||A||_F^2; subspace: pivot, residual,

@@ -128,3 +128,40 @@ def test_missing_device_path_is_loud():
     with pytest.raises(BubbleConError):
         e.run(np.array([99, 0, 0], dtype=np.int64))   # unknown opcode before reserve -> error, not silence
     e.close()
+
+
+def test_robust_bp_retry_and_random_messages():
+    """robust_belief_propagation's retry path (trunc_dim x 1.5, +11 iterations, fresh messages: reference :285-350) and random
+    quantum initial messages run on the device and end converged."""
+    D, N = 2, 2
+    cell = UnitCell.random(2, D, seed=21)
+    tn = bp.KagomeTNRepeatedUnitCell(cell, N)
+    cfg = BPConfig(trunc_dim=2 * D * D, msg_diff_terminate=1e-7, msg_diff_good_enough=1e-5, damping=0.1, init_msg="UQ",
+                   max_iterations=3, allowed_retries=3)
+    tn.connect_uniform_messages()
+    msgs, stats = bp.robust_belief_propagation(tn, tn.messages, cfg)
+    assert stats.attempts >= 2                      # 3 iterations are not enough: the first attempt must fail
+    assert stats.final_error < 1e-5 and stats.success
+    rng = np.random.RandomState(4)
+    tn2 = bp.KagomeTNRepeatedUnitCell(cell, N)
+    tn2.connect_random_messages(rng)
+    cfg2 = BPConfig(trunc_dim=2 * D * D, msg_diff_terminate=1e-7, damping=None, init_msg="RQ", hermitize_msgs_when_finished=False)
+    m2, st2 = bp.belief_propagation(tn2, tn2.messages, cfg2)
+    assert st2.success and st2.final_error < 1e-7
+    # both runs describe the same fixed point (the first one only to msg_diff_good_enough)
+    for side in SIDES:
+        assert overlap_defect(to_oracle_mps(msgs[side].mps), to_oracle_mps(m2[side].mps)) < 1e-3
+
+
+def test_nonfinite_input_raises():
+    """the reference prints and exits on nan/inf in the boundary MPS (src/libs/bmpslib.py:711-717): here BubbleConError."""
+    from kagomeperiodicbp_b200.engine import BubbleConError
+    D, N = 2, 2
+    cell = UnitCell.random(2, D, seed=3)
+    bad = UnitCell(cell.A.copy(), cell.B.copy(), cell.C.copy())
+    bad.A[0, 0, 0, 0, 0] = np.nan
+    tn = bp.KagomeTNRepeatedUnitCell(bad, N)
+    tn.connect_uniform_messages()
+    cfg = BPConfig(trunc_dim=8, msg_diff_terminate=1e-6, damping=0.1, init_msg="UQ")
+    with pytest.raises(BubbleConError):
+        bp.bp_step_batch(N, [bad], [tn.messages], cfg)

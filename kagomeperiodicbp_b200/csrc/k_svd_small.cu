@@ -19,8 +19,12 @@
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+namespace cg = cooperative_groups;
 
 namespace kbp {
 
@@ -28,11 +32,52 @@ constexpr double SMALL_TOL = 1e-14;
 constexpr int SMALL_MAX_SWEEPS = 60;
 constexpr size_t SMALL_SMEM_MAX = 225 * 1024;
 
-__device__ __forceinline__ void rr_pair_s(int n, int r, int t, int& a, int& b) {
-  const int m = n - 1;
-  if (t == 0) { a = m; b = r; }
-  else { a = (r + t) % m; b = (r - t + m) % m; }
-  if (a > b) { int x = a; a = b; b = x; }
+// Round-robin tournament on pp (even) players: in step r, slot 0 pairs player pp-1 with r, slot t > 0 pairs (r + t) mod (pp-1)
+// with (r - t) mod (pp-1).  The two residues are carried from step to step (no integer division in the step loop).
+struct PairWalk {
+  int ra, rb, m1, slot;
+  __device__ __forceinline__ void start(int pp, int slot_) { m1 = pp - 1; slot = slot_; ra = slot_; rb = slot_ == 0 ? 0 : m1 - slot_; }
+  __device__ __forceinline__ void get(int step, int& i, int& j) const {
+    if (slot == 0) { i = step; j = m1; }
+    else { i = ra < rb ? ra : rb; j = ra < rb ? rb : ra; }
+  }
+  __device__ __forceinline__ void next() { ra = ra + 1 == m1 ? 0 : ra + 1; rb = rb + 1 == m1 ? 0 : rb + 1; }
+};
+
+template <int G>
+__device__ __forceinline__ void group_sum4(double& a, double& b, double& cr, double& ci, unsigned gmask) {
+#pragma unroll
+  for (int o = G >> 1; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(gmask, a, o);
+    b += __shfl_xor_sync(gmask, b, o);
+    cr += __shfl_xor_sync(gmask, cr, o);
+    ci += __shfl_xor_sync(gmask, ci, o);
+  }
+}
+
+// The rotation that orthogonalises rows x_i, x_j with Gram entries a = |x_i|^2, b = |x_j|^2, c = <x_i, x_j> = cr + i ci:
+// x_j' = e x_j with e = c/|c| makes the inner product real, then a real rotation by theta, tan(2 theta) = 2|c| / (a - b),
+// |theta| <= pi/4.  With h = (a-b)^2 + 4|c|^2:  cos^2(theta) = (1 + |a-b|/sqrt(h)) / 2,  sin(theta) = |c| / (sqrt(h) cos(theta)):
+// two levels of special functions (rsqrt(|c|^2) || rsqrt(h), then rsqrt(cos^2)) and no division; products only, so a tiny
+// |c| keeps its relative accuracy.  Returns false when the pair is already orthogonal to tolerance (or a row is dead).
+// `big` is raised when cos^2 of the pair's angle exceeded SMALL_TOL (the sweep-level convergence test).
+struct Rotation { double cs, sn, er, ei; bool swap; };
+__device__ __forceinline__ bool make_rotation(double a, double b, double cr, double ci, double floor2, bool& big, Rotation& R) {
+  const double r2 = fma(cr, cr, ci * ci), ab = a * b;
+  if (!(a > floor2 && b > floor2 && r2 > (SMALL_TOL * SMALL_TOL) * ab)) return false;
+  big = big || r2 > SMALL_TOL * ab;
+  const double d = a - b;
+  const double h = fma(d, d, 4.0 * r2);
+  const double ri = rsqrt(r2), rh = rsqrt(h);
+  const double x = fma(0.5 * fabs(d), rh, 0.5);
+  const double rs = rsqrt(x);
+  const double sn = (r2 * ri) * rh * rs;
+  R.cs = x * rs;
+  R.sn = d < 0.0 ? -sn : sn;
+  R.er = cr * ri;
+  R.ei = ci * ri;
+  R.swap = d < 0.0;                                  // keep the larger row first (de Rijk)
+  return true;
 }
 
 struct SmallArgs {
@@ -53,9 +98,9 @@ bool svd_small_fits(int64_t m, int64_t n) {
 }
 
 // rotate one row pair with both rows held in registers between the Gram sums and the update (CPL columns per lane)
-template <int CPL>
-__device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int qx, int G, int gl, unsigned gmask,
-                                                   double floor2, double& my_off) {
+template <int CPL, int G>
+__device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int qx, int gl, unsigned gmask,
+                                                   double floor2, bool& big) {
   cplx u[CPL], v[CPL];
   double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
 #pragma unroll
@@ -66,44 +111,27 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
     if (c < qx) {                                  // Gram sums over the data columns only (not the accumulated rotations)
       a = fma(u[k].x, u[k].x, fma(u[k].y, u[k].y, a));
       b = fma(v[k].x, v[k].x, fma(v[k].y, v[k].y, b));
-      cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));
+      cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));          // u conj(v)
       ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
     }
   }
-  for (int o = G >> 1; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(gmask, a, o);
-    b += __shfl_xor_sync(gmask, b, o);
-    cr += __shfl_xor_sync(gmask, cr, o);
-    ci += __shfl_xor_sync(gmask, ci, o);
-  }
-  const double r2 = fma(cr, cr, ci * ci);
-  if (!(a > floor2 && b > floor2 && r2 > 0.0)) return;
-  // the pair counts as unconverged iff |c|^2 > tol^2 a b (no division / square root on the decision path); the rotation
-  // needs three dependent special-function evaluations: rsqrt(|c|^2) || rsqrt(d^2 + 4|c|^2), a reciprocal, rsqrt(1 + t^2)
-  if (!(r2 > (SMALL_TOL * SMALL_TOL) * a * b)) return;
-  my_off = fmax(my_off, r2 * __drcp_rn(a * b));        // cos^2 of the pair's angle (off the rotation's critical path)
-  const double inv = rsqrt(r2), ab = r2 * inv;
-  const double er = cr * inv, ei = ci * inv;
-  const double d = a - b;
-  const double h = fma(d, d, 4.0 * r2);
-  double tt = 2.0 * ab * __drcp_rn(fabs(d) + h * rsqrt(h));
-  if (d < 0.0) tt = -tt;
-  const double cs = rsqrt(fma(tt, tt, 1.0)), sn = tt * cs;
-  const bool swap = d < 0.0;
+  group_sum4<G>(a, b, cr, ci, gmask);
+  Rotation R;
+  if (!make_rotation(a, b, cr, ci, floor2, big, R)) return;
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int c = gl + k * G;
     if (c < q) {
-      const double vr = er * v[k].x - ei * v[k].y, vi = er * v[k].y + ei * v[k].x;
-      const cplx yi = make_double2(fma(cs, u[k].x, sn * vr), fma(cs, u[k].y, sn * vi));
-      const cplx yj = make_double2(fma(cs, vr, -sn * u[k].x), fma(cs, vi, -sn * u[k].y));
-      xi[c] = swap ? yj : yi;
-      xj[c] = swap ? yi : yj;
+      const double vr = R.er * v[k].x - R.ei * v[k].y, vi = R.er * v[k].y + R.ei * v[k].x;     // e x_j
+      const cplx yi = make_double2(fma(R.cs, u[k].x, R.sn * vr), fma(R.cs, u[k].y, R.sn * vi));
+      const cplx yj = make_double2(fma(R.cs, vr, -R.sn * u[k].x), fma(R.cs, vi, -R.sn * u[k].y));
+      xi[c] = R.swap ? yj : yi;
+      xj[c] = R.swap ? yi : yj;
     }
   }
 }
 
-template <bool CACHED>
+template <bool CACHED, int G>
 __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
                                                                         int n_slots, SmallArgs g) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -114,7 +142,6 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   double* s2 = reinterpret_cast<double*>(sm_raw + sizeof(cplx) * (size_t)p * q);   // p
   int* idx = reinterpret_cast<int*>(s2 + p);                                 // p
   __shared__ double red[34];
-  __shared__ double sh_flag;
 
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
   const cplx* A = cb + g.A;
@@ -144,95 +171,65 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   const double floor2 = 1e-34 * fro2;
 
   // ---- Jacobi sweeps
-  const int pp = (p + 1) & ~1, npairs = pp / 2, G = g.group;
+  const int pp = (p + 1) & ~1, npairs = pp / 2;
   const int slot = t / G, gl = t - slot * G;
   // groups of one warp can take different branches (phantom row, dead rows): shuffles name their own group only
   const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int cpl = (q + G - 1) / G;
   bool converged = p < 2;
 #ifdef KBP_SMALL_DEBUG
-  int nsweeps = 0;
   long long tstart = clock64();
 #endif
   for (int sweep = 0; sweep < SMALL_MAX_SWEEPS && !converged; ++sweep) {
-#ifdef KBP_SMALL_DEBUG
-    ++nsweeps;
-#endif
-    double my_off = 0.0;
+    bool big = false;
+    PairWalk walk;
+    walk.start(pp, slot);
     for (int step = 0; step < pp - 1; ++step) {
-      if (slot < npairs) {
-        int i, j;
-        rr_pair_s(pp, step, slot, i, j);
-        if (CACHED && j < p) {
-          cplx* xi = X + i * q;
-          cplx* xj = X + j * q;
-          switch ((q + G - 1) / G) {
-            case 1: jacobi_pair_cached<1>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
-            case 2: jacobi_pair_cached<2>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
-            case 3: jacobi_pair_cached<3>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
-            case 4: jacobi_pair_cached<4>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
-            case 5: jacobi_pair_cached<5>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
-            default: jacobi_pair_cached<6>(xi, xj, q, qx, G, gl, gmask, floor2, my_off); break;
+      int i, j;
+      walk.get(step, i, j);
+      if (slot < npairs && j < p) {
+        cplx* xi = X + i * q;
+        cplx* xj = X + j * q;
+        if (CACHED) {
+          switch (cpl) {
+            case 1: jacobi_pair_cached<1, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            case 2: jacobi_pair_cached<2, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            case 3: jacobi_pair_cached<3, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            case 4: jacobi_pair_cached<4, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            case 5: jacobi_pair_cached<5, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            default: jacobi_pair_cached<6, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
           }
-        } else if (j < p) {
-          cplx* xi = X + i * q;
-          cplx* xj = X + j * q;
+        } else {
           double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
           for (int c = gl; c < qx; c += G) {
             const cplx u = xi[c], v = xj[c];
             a = fma(u.x, u.x, fma(u.y, u.y, a));
             b = fma(v.x, v.x, fma(v.y, v.y, b));
-            cr = fma(u.x, v.x, fma(u.y, v.y, cr));          // u conj(v)
+            cr = fma(u.x, v.x, fma(u.y, v.y, cr));
             ci = fma(u.y, v.x, fma(-u.x, v.y, ci));
           }
-          for (int o = G >> 1; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(gmask, a, o);
-            b += __shfl_xor_sync(gmask, b, o);
-            cr += __shfl_xor_sync(gmask, cr, o);
-            ci += __shfl_xor_sync(gmask, ci, o);
-          }
-          const double r2 = fma(cr, cr, ci * ci);
-          if (a > floor2 && b > floor2 && r2 > 0.0) {
-            if (r2 > (SMALL_TOL * SMALL_TOL) * a * b) {
-              my_off = fmax(my_off, r2 * __drcp_rn(a * b));
-              // x_j' = e x_j with e = c/|c| makes <x_i, x_j'> = |c| real; then a real rotation by theta,
-              // tan(2 theta) = 2|c| / (a - b), small-angle root
-              const double inv = rsqrt(r2), ab = r2 * inv;
-              const double er = cr * inv, ei = ci * inv;
-              const double d = a - b;
-              const double h = fma(d, d, 4.0 * r2);
-              double tt = 2.0 * ab * __drcp_rn(fabs(d) + h * rsqrt(h));
-              if (d < 0.0) tt = -tt;
-              const double cs = rsqrt(fma(tt, tt, 1.0)), sn = tt * cs;
-              const bool swap = d < 0.0;            // keep the larger row first
-              for (int c = gl; c < q; c += G) {
-                const cplx u = xi[c], v = xj[c];
-                const double vr = er * v.x - ei * v.y, vi = er * v.y + ei * v.x;     // e x_j
-                const cplx yi = make_double2(fma(cs, u.x, sn * vr), fma(cs, u.y, sn * vi));
-                const cplx yj = make_double2(fma(cs, vr, -sn * u.x), fma(cs, vi, -sn * u.y));
-                xi[c] = swap ? yj : yi;
-                xj[c] = swap ? yi : yj;
-              }
+          group_sum4<G>(a, b, cr, ci, gmask);
+          Rotation R;
+          if (make_rotation(a, b, cr, ci, floor2, big, R)) {
+            for (int c = gl; c < q; c += G) {
+              const cplx u = xi[c], v = xj[c];
+              const double vr = R.er * v.x - R.ei * v.y, vi = R.er * v.y + R.ei * v.x;
+              const cplx yi = make_double2(fma(R.cs, u.x, R.sn * vr), fma(R.cs, u.y, R.sn * vi));
+              const cplx yj = make_double2(fma(R.cs, vr, -R.sn * u.x), fma(R.cs, vi, -R.sn * u.y));
+              xi[c] = R.swap ? yj : yi;
+              xj[c] = R.swap ? yi : yj;
             }
           }
         }
       }
+      walk.next();
       __syncthreads();
     }
-    // sweep-wide maximum of the pair measure
-    my_off = warp_max(my_off);
-    if (lane == 0) red[w] = my_off;
-    __syncthreads();
-    if (w == 0) {
-      double x = lane < nw ? red[lane] : 0.0;
-      x = warp_max(x);
-      if (lane == 0) sh_flag = x;
-    }
-    __syncthreads();
-    // my_off = largest cos^2 rotated away in this sweep (0: nothing was above tol).  One-sided Jacobi converges quadratically
-    // at the end: once every pair of a sweep started below sqrt(tol), the next sweep would find nothing to do -- skip it
-    converged = sh_flag <= SMALL_TOL;
+    // One-sided Jacobi converges quadratically at the end: once every pair of a sweep started with cos^2 <= tol, the next
+    // sweep would find nothing to do -- skip it.  (`big`: some pair of this sweep was above that.)
+    converged = !__syncthreads_or(big ? 1 : 0);
 #ifdef KBP_SMALL_DEBUG
-    if (t == 0) printf("[small %dx%d] sweep %d max off %.3e  cycles %lld\n", p, q, sweep, sh_flag, clock64() - tstart);
+    if (t == 0) printf("[small %dx%d] sweep %d converged %d  cycles %lld\n", p, q, sweep, (int)converged, clock64() - tstart);
 #endif
   }
 
@@ -268,7 +265,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
       const double sk2 = s2[idx[k]];
       Vh[e] = sk2 > floor2 ? cscale(X[idx[k] * q + c], rsqrt(sk2)) : cmake(0.0, 0.0);
     }
-    for (int e = w; e < m * keep; e += nw) {
+    for (int e = w; g.US >= 0 && e < m * keep; e += nw) {
       const int r = e / keep, k = e - r * keep;
       const double sk2 = s2[idx[k]];
       const cplx* xr = X + idx[k] * q;
@@ -280,7 +277,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
     }
   } else {
     // US_k = data part of the rows ;  Vh_k = conj of the accumulated-rotation part (orthonormal to rounding)
-    for (int e = t; e < m * keep; e += nt) {
+    for (int e = t; g.US >= 0 && e < m * keep; e += nt) {
       const int r = e / keep, k = e - r * keep;
       US[e] = cscale(X[idx[k] * q + r], scale);
     }
@@ -297,18 +294,283 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same factorisation on a thread-block CLUSTER: the one-CTA kernel above is bound by the FP64 rate of a single SM
+// (all pp/2 pair rotations of a step run there).  Here C CTAs (C SMs) share one matrix by COLUMNS: CTA r keeps columns
+// [r ql, (r+1) ql) of every row in its shared memory.  A step is
+//   partial Gram sums of each pair over the local columns -> pushed into every CTA's shared memory (DSMEM stores)
+//   -> one cluster barrier -> every CTA adds the C partials in rank order (bitwise identical totals, so all CTAs take
+//   the same decisions and build the same rotation) -> rotates its own columns.
+// Per-SM arithmetic drops ~C-fold for the sums and the updates; the rotation itself (three special-function chains) is
+// recomputed everywhere.  The price is one cluster barrier (~400 cycles) + 32 B x pairs x C of DSMEM traffic per step.
+struct __align__(16) PairSums { double a, b, cr, ci; };
+constexpr int CL_C = 4;     // CTAs per cluster
+constexpr int CL_G = 8;     // lanes per row pair
+
+template <int CPL>
+__global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
+                                                           int n_slots, SmallArgs g) {
+  constexpr int C = CL_C, G = CL_G;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int m = g.m, n = g.n;
+  const bool mode_t = m > n;
+  const int p = mode_t ? n : m, qx = mode_t ? m : n, q = mode_t ? m + n : n;
+  const int ql = (q + C - 1) / C, c0 = rank * ql;                       // this CTA's column slice [c0, c0 + qn)
+  const int qn = max(0, min(ql, q - c0)), qxn = max(0, min(qn, qx - c0));     // qxn: local columns that are data (enter the Gram sums)
+  const int pp = (p + 1) & ~1, npairs = pp / 2;
+  cplx* X = reinterpret_cast<cplx*>(sm_raw);                                    // p x ql
+  PairSums* part = reinterpret_cast<PairSums*>(sm_raw + sizeof(cplx) * (size_t)p * ql);   // [2][C][npairs]
+  double* s2p = reinterpret_cast<double*>(part + 2 * C * npairs);                // [C][p]
+  double* s2 = s2p + C * p;                                                     // p
+  int* idx = reinterpret_cast<int*>(s2 + p);                                    // p
+  __shared__ double red[34];
+
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const cplx* A = cb + g.A;
+  cplx* US = cb + g.US;
+  cplx* Vh = cb + g.Vh;
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, w = t >> 5, nw = nt >> 5;
+
+  // ---- load this CTA's columns; ||A||_F^2 over the whole matrix in every CTA (same order -> same value everywhere)
+  if (!mode_t) {
+    for (int e = t; e < p * qn; e += nt) {
+      const int r = e / qn, cl = e - r * qn;
+      X[r * ql + cl] = A[(long long)r * g.lda + c0 + cl];
+    }
+  } else {
+    for (int e = t; e < p * qn; e += nt) {
+      const int cl = e / p, r = e - cl * p, c = c0 + cl;                    // row r of X = column r of A, then row r of I
+      X[r * ql + cl] = c < m ? A[(long long)c * g.lda + r] : cmake(c - m == r ? 1.0 : 0.0, 0.0);
+    }
+  }
+  double fro = 0.0;
+  for (int e = t; e < m * n; e += nt) fro += cabs2(A[(long long)(e / n) * g.lda + e % n]);
+  const double fro2 = block_sum(fro, red);
+  const double floor2 = 1e-34 * fro2;
+
+  const int slot = t / G, gl = t - slot * G;
+  const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
+  // where lane gl < C delivers this CTA's partial sums: CTA gl's copy of part[.][rank][slot]
+  PairSums* remote = cluster.map_shared_rank(part + rank * npairs + (slot < npairs ? slot : 0), gl < C ? gl : 0);
+  bool converged = p < 2;
+  int tick = 0;
+#ifdef KBP_SMALL_DEBUG
+  long long tstart = clock64();
+  long long ph[4] = {0, 0, 0, 0};
+#endif
+  cluster.sync();                                   // every CTA of the cluster is resident before the first remote store
+  for (int sweep = 0; sweep < SMALL_MAX_SWEEPS && !converged; ++sweep) {
+    bool big = false;
+    PairWalk walk;
+    walk.start(pp, slot);
+    for (int step = 0; step < pp - 1; ++step) {
+#ifdef KBP_SMALL_DEBUG
+      const long long k0 = clock64();
+#endif
+      int i, j;
+      walk.get(step, i, j);
+      const bool act = slot < npairs && j < p;
+      cplx u[CPL], v[CPL];
+      cplx* xi = X + i * ql;
+      cplx* xj = X + j * ql;
+      if (act) {
+        double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+          const int cl = gl + k * G;
+          u[k] = cl < qn ? xi[cl] : cmake(0.0, 0.0);
+          v[k] = cl < qn ? xj[cl] : cmake(0.0, 0.0);
+          if (cl < qxn) {
+            a = fma(u[k].x, u[k].x, fma(u[k].y, u[k].y, a));
+            b = fma(v[k].x, v[k].x, fma(v[k].y, v[k].y, b));
+            cr = fma(u[k].x, v[k].x, fma(u[k].y, v[k].y, cr));
+            ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
+          }
+        }
+        group_sum4<G>(a, b, cr, ci, gmask);
+        if (gl < C) {
+          PairSums ps;
+          ps.a = a; ps.b = b; ps.cr = cr; ps.ci = ci;
+          remote[tick * C * npairs] = ps;
+        }
+      }
+#ifdef KBP_SMALL_DEBUG
+      const long long k1 = clock64();
+#endif
+      cluster.sync();
+#ifdef KBP_SMALL_DEBUG
+      const long long k2 = clock64();
+#endif
+      if (act) {
+        const PairSums* ps = part + tick * C * npairs + slot;
+        double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
+#pragma unroll
+        for (int r = 0; r < C; ++r) { a += ps[r * npairs].a; b += ps[r * npairs].b; cr += ps[r * npairs].cr; ci += ps[r * npairs].ci; }
+        Rotation R;
+        if (make_rotation(a, b, cr, ci, floor2, big, R)) {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) {
+            const int cl = gl + k * G;
+            if (cl < qn) {
+              const double vr = R.er * v[k].x - R.ei * v[k].y, vi = R.er * v[k].y + R.ei * v[k].x;
+              const cplx yi = make_double2(fma(R.cs, u[k].x, R.sn * vr), fma(R.cs, u[k].y, R.sn * vi));
+              const cplx yj = make_double2(fma(R.cs, vr, -R.sn * u[k].x), fma(R.cs, vi, -R.sn * u[k].y));
+              xi[cl] = R.swap ? yj : yi;
+              xj[cl] = R.swap ? yi : yj;
+            }
+          }
+        }
+      }
+      tick ^= 1;
+      walk.next();
+#ifdef KBP_SMALL_DEBUG
+      const long long k3 = clock64();
+#endif
+      __syncthreads();
+#ifdef KBP_SMALL_DEBUG
+      const long long k4 = clock64();
+      ph[0] += k1 - k0; ph[1] += k2 - k1; ph[2] += k3 - k2; ph[3] += k4 - k3;
+#endif
+    }
+    converged = !__syncthreads_or(big ? 1 : 0);     // identical in every CTA: same totals, same decisions
+#ifdef KBP_SMALL_DEBUG
+    if (t == 0 && rank == 0) printf("[cluster %dx%d C %d G %d] sweep %d converged %d  cycles %lld  phases: dots %lld barrier %lld rotate %lld sync %lld\n", p, q, C, G, sweep, (int)converged, clock64() - tstart, ph[0], ph[1], ph[2], ph[3]);
+#endif
+  }
+
+  // ---- singular values: partial row norms -> every CTA, summed in rank order
+  for (int i = w; i < p; i += nw) {
+    double acc = 0.0;
+    const cplx* row = X + i * ql;
+    for (int cl = lane; cl < qxn; cl += 32) acc += cabs2(row[cl]);
+    acc = warp_sum(acc);
+    if (lane < C) *cluster.map_shared_rank(s2p + rank * p + i, lane) = acc;
+  }
+  cluster.sync();
+  for (int i = t; i < p; i += nt) {
+    double acc = 0.0;
+    for (int r = 0; r < C; ++r) acc += s2p[r * p + i];
+    s2[i] = (acc == acc && acc < 1e300) ? acc : 0.0;
+    idx[i] = i;
+  }
+  __syncthreads();
+  double disc_part = 0.0;
+  for (int i = t; i < p; i += nt) {
+    const double si = s2[i];
+    int rk = 0;
+    for (int j = 0; j < p; ++j) {
+      const double sj = s2[j];
+      rk += (sj > si) || (sj == si && j < i);
+    }
+    if (rk >= g.keep) disc_part += si;
+    idx[rk] = i;
+  }
+  const double disc = block_sum(disc_part, red);
+  const double frob = sqrt(fro2);
+  const double scale = (g.nr_bulk && frob > 0.0) ? 1.0 / frob : 1.0;
+  const int keep = g.keep;
+  if (!mode_t) {
+    for (int e = t; e < keep * qn; e += nt) {
+      const int k = e / qn, cl = e - k * qn;
+      const double sk2 = s2[idx[k]];
+      Vh[(long long)k * n + c0 + cl] = sk2 > floor2 ? cscale(X[idx[k] * ql + cl], rsqrt(sk2)) : cmake(0.0, 0.0);
+    }
+    if (g.US >= 0) {
+      // US = A Vh_k^H needs whole rows of Vh: publish them, then CTA r takes the rows r, r + C, ... of US
+      __threadfence();
+      cluster.sync();
+      for (int e = w; e < m * keep; e += nw) {
+        const int r = e / keep, k = e - r * keep;
+        if (r % C != rank) continue;
+        const cplx* ar = A + (long long)r * g.lda;
+        const cplx* vr = Vh + (long long)k * n;
+        cplx acc = cmake(0.0, 0.0);
+        for (int c = lane; c < n; c += 32) acc = cadd(acc, cmulc(ar[c], __ldcg(vr + c)));
+        acc = warp_sum(acc);
+        if (lane == 0) US[e] = cscale(acc, scale);
+      }
+    }
+  } else {
+    for (int e = t; e < keep * qn; e += nt) {
+      const int k = e / qn, cl = e - k * qn, c = c0 + cl;
+      const cplx x = X[idx[k] * ql + cl];
+      if (c < m) { if (g.US >= 0) US[(long long)c * keep + k] = cscale(x, scale); }
+      else Vh[(long long)k * n + (c - m)] = s2[idx[k]] > floor2 ? cconj(x) : cmake(0.0, 0.0);
+    }
+  }
+  if (t == 0 && rank == 0) {
+    double* sl = slots + (long long)blockIdx.y * n_slots;
+    if (g.nr_bulk && g.slot_lognorm >= 0 && frob > 0.0) sl[g.slot_lognorm] += log(frob);
+    if (g.slot_trunc >= 0 && fro2 > 0.0) sl[g.slot_trunc] += sqrt(disc / fro2);
+    if (!converged) sl[n_slots - 1] += 1.0;
+  }
+}
+
+template <int CPL>
+static cudaError_t launch_cluster(const Arena& a, const SmallArgs& g, int C, int threads, size_t smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(svd_cluster_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)C, (unsigned)a.nb);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, svd_cluster_kernel<CPL>, a.base, (long long)a.chain_stride, a.slots, a.n_slots, g);
+}
+
 void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
                int slot_lognorm, int slot_trunc) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(svd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_small_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
     attr_set = true;
   }
   SmallArgs g;
   g.A = A; g.US = US; g.Vh = Vh; g.m = (int)m; g.n = (int)n; g.lda = (int)lda; g.keep = (int)keep;
   g.nr_bulk = nr_bulk; g.slot_lognorm = slot_lognorm; g.slot_trunc = slot_trunc;
   const int p = (int)(m < n ? m : n), pp = (p + 1) & ~1, npairs = pp / 2 > 0 ? pp / 2 : 1;
+  const int q = (int)(m <= n ? n : m + n);
+  // cluster version for the larger matrices (KBP_SMALL_CLUSTER=0: off; KBP_SMALL_CLUSTER_MINP = smallest p that uses it)
+  static const bool cluster_on = !(getenv("KBP_SMALL_CLUSTER") && atoi(getenv("KBP_SMALL_CLUSTER")) == 0);
+  static const int cluster_minp = getenv("KBP_SMALL_CLUSTER_MINP") ? atoi(getenv("KBP_SMALL_CLUSTER_MINP")) : 48;
+  if (cluster_on && p >= cluster_minp) {
+    const int C = CL_C, ql = (q + C - 1) / C, cpl = (ql + CL_G - 1) / CL_G;
+    if (cpl <= 6 && npairs * CL_G <= 1024) {
+      g.group = CL_G;
+      int threads = (npairs * CL_G + 31) / 32 * 32;
+      if (threads < 128) threads = 128;
+      const size_t smem = sizeof(double2) * (size_t)p * ql + sizeof(PairSums) * 2 * (size_t)C * npairs +
+                          sizeof(double) * ((size_t)C * p + p) + sizeof(int) * (size_t)p + 64;
+      cudaError_t e = cudaSuccess;
+      switch (cpl) {
+        case 1: e = launch_cluster<1>(a, g, C, threads, smem); break;
+        case 2: e = launch_cluster<2>(a, g, C, threads, smem); break;
+        case 3: e = launch_cluster<3>(a, g, C, threads, smem); break;
+        case 4: e = launch_cluster<4>(a, g, C, threads, smem); break;
+        case 5: e = launch_cluster<5>(a, g, C, threads, smem); break;
+        default: e = launch_cluster<6>(a, g, C, threads, smem); break;
+      }
+      if (e == cudaSuccess) { ++*a.launches; return; }
+      cudaGetLastError();                           // cluster launch refused: use the one-CTA kernel
+    }
+  }
   int G = 32;
   while (G > 8 && npairs * G > 1024) G >>= 1;
   g.group = G;
@@ -316,11 +578,13 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
   threads = (threads + 31) / 32 * 32;
   if (threads < 256) threads = 256;
   if (threads > 1024) threads = 1024;
-  const int q = (int)(m <= n ? n : m + n);
-  if (threads <= 768 && (q + G - 1) / G <= 6)
-    svd_small_kernel<true><<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
-  else
-    svd_small_kernel<false><<<a.nb, threads, svd_small_smem(m, n), a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g);
+  const bool cached = threads <= 768 && (q + G - 1) / G <= 6;
+  const size_t smem = svd_small_smem(m, n);
+#define KBP_SMALL_LAUNCH(CA, GG) svd_small_kernel<CA, GG><<<a.nb, threads, smem, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, g)
+  if (G == 32) { if (cached) KBP_SMALL_LAUNCH(true, 32); else KBP_SMALL_LAUNCH(false, 32); }
+  else if (G == 16) { if (cached) KBP_SMALL_LAUNCH(true, 16); else KBP_SMALL_LAUNCH(false, 16); }
+  else { if (cached) KBP_SMALL_LAUNCH(true, 8); else KBP_SMALL_LAUNCH(false, 8); }
+#undef KBP_SMALL_LAUNCH
   ++*a.launches;
 }
 

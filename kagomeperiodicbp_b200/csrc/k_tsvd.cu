@@ -564,7 +564,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
       gemm(a, Rm, R2, R1, b, b, b, OP_N, OP_N);                       // W = Y (R2 R1)
       Rsmall = Rm;
     }
-    svd_small(a, Rsmall, b, USs, Vbs, b, b, b, 0, -1, -1);            // Vbs = Vb^H (b x b), rows by decreasing singular value
+    svd_small(a, Rsmall, b, -1, Vbs, b, b, b, 0, -1, -1);             // Vbs = Vb^H (b x b), rows by decreasing singular value
     gemm(a, Vh, Vbs, Qb, keep, n, b, OP_N, OP_C);                     // Vh = Vb_k^H Q^H
     phase_fix(a, Vh, US, m, n, keep, 0);                              // canonical gauge of the kept bond
     gemm(a, US, A, Vh, m, keep, n, OP_N, OP_C);                       // US = A Vh^H

@@ -44,16 +44,28 @@ struct PairWalk {
   __device__ __forceinline__ void next() { ra = ra + 1 == m1 ? 0 : ra + 1; rb = rb + 1 == m1 ? 0 : rb + 1; }
 };
 
+struct __align__(16) PairSums { double a, b, cr, ci; };
+
+// Sum (a, b, cr, ci) over the G lanes of a group and hand all four totals to every lane.  Shuffles are the scarce resource
+// here (one warp-shuffle per 4 cycles per SM sub-partition, two per double), so the butterfly is TRANSPOSED: the first two
+// stages halve the number of values a lane carries (4 -> 2 -> 1) while doubling what each covers, the remaining stages
+// reduce that single value: 4 + log2(G/4) double-shuffles instead of 4 log2(G).  The four owners then publish the totals
+// through a 32-byte shared-memory record of the pair, which every lane reads back (broadcast loads).
 template <int G>
-__device__ __forceinline__ void group_sum4(double& a, double& b, double& cr, double& ci, unsigned gmask) {
+__device__ __forceinline__ double group_reduce4(double a, double b, double cr, double ci, int gl, unsigned gmask) {
+  static_assert(G >= 4, "group of at least 4 lanes");
+  const bool b0 = gl & 1, b1 = gl & 2;
+  double k0 = b0 ? cr : a, k1 = b0 ? ci : b;                       // even lanes keep (a, b), odd lanes keep (cr, ci)
+  k0 += __shfl_xor_sync(gmask, b0 ? a : cr, 1);
+  k1 += __shfl_xor_sync(gmask, b0 ? b : ci, 1);
+  double mine = b1 ? k1 : k0;                                      // (b1, b0) = 00: a   01: cr   10: b   11: ci
+  mine += __shfl_xor_sync(gmask, b1 ? k0 : k1, 2);
 #pragma unroll
-  for (int o = G >> 1; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(gmask, a, o);
-    b += __shfl_xor_sync(gmask, b, o);
-    cr += __shfl_xor_sync(gmask, cr, o);
-    ci += __shfl_xor_sync(gmask, ci, o);
-  }
+  for (int o = 4; o < G; o <<= 1) mine += __shfl_xor_sync(gmask, mine, o);
+  return mine;
 }
+// position of lane gl's total inside PairSums {a, b, cr, ci}
+__device__ __forceinline__ int owner_pos(int gl) { return ((gl & 1) << 1) | ((gl >> 1) & 1); }
 
 // The rotation that orthogonalises rows x_i, x_j with Gram entries a = |x_i|^2, b = |x_j|^2, c = <x_i, x_j> = cr + i ci:
 // x_j' = e x_j with e = c/|c| makes the inner product real, then a real rotation by theta, tan(2 theta) = 2|c| / (a - b),
@@ -89,7 +101,7 @@ struct SmallArgs {
 
 size_t svd_small_smem(int64_t m, int64_t n) {
   const int64_t p = m < n ? m : n, q = m <= n ? n : m + n;       // tall: rows of [A^T | I]
-  return (size_t)(p * q) * sizeof(double2) + (size_t)p * (sizeof(double) + sizeof(int)) + 64;
+  return (size_t)(p * q) * sizeof(double2) + (size_t)p * (sizeof(double) + sizeof(int)) + 16 + (size_t)((p + 1) / 2) * sizeof(PairSums) + 64;
 }
 
 bool svd_small_fits(int64_t m, int64_t n) {
@@ -100,7 +112,7 @@ bool svd_small_fits(int64_t m, int64_t n) {
 // rotate one row pair with both rows held in registers between the Gram sums and the update (CPL columns per lane)
 template <int CPL, int G>
 __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* __restrict__ xj, int q, int qx, int gl, unsigned gmask,
-                                                   double floor2, bool& big) {
+                                                   double floor2, bool& big, PairSums* __restrict__ rec) {
   cplx u[CPL], v[CPL];
   double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
 #pragma unroll
@@ -115,9 +127,12 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
       ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
     }
   }
-  group_sum4<G>(a, b, cr, ci, gmask);
+  const double mine = group_reduce4<G>(a, b, cr, ci, gl, gmask);
+  if (gl < 4) reinterpret_cast<double*>(rec)[owner_pos(gl)] = mine;
+  __syncwarp(gmask);
+  const PairSums tot = *rec;
   Rotation R;
-  if (!make_rotation(a, b, cr, ci, floor2, big, R)) return;
+  if (!make_rotation(tot.a, tot.b, tot.cr, tot.ci, floor2, big, R)) return;
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int c = gl + k * G;
@@ -141,6 +156,7 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
   cplx* X = reinterpret_cast<cplx*>(sm_raw);                                 // p x q
   double* s2 = reinterpret_cast<double*>(sm_raw + sizeof(cplx) * (size_t)p * q);   // p
   int* idx = reinterpret_cast<int*>(s2 + p);                                 // p
+  PairSums* rec = reinterpret_cast<PairSums*>(sm_raw + ((sizeof(cplx) * (size_t)p * q + (size_t)p * 12 + 15) & ~(size_t)15));   // (p+1)/2 pair records
   __shared__ double red[34];
 
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
@@ -192,12 +208,12 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
         cplx* xj = X + j * q;
         if (CACHED) {
           switch (cpl) {
-            case 1: jacobi_pair_cached<1, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
-            case 2: jacobi_pair_cached<2, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
-            case 3: jacobi_pair_cached<3, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
-            case 4: jacobi_pair_cached<4, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
-            case 5: jacobi_pair_cached<5, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
-            default: jacobi_pair_cached<6, G>(xi, xj, q, qx, gl, gmask, floor2, big); break;
+            case 1: jacobi_pair_cached<1, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
+            case 2: jacobi_pair_cached<2, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
+            case 3: jacobi_pair_cached<3, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
+            case 4: jacobi_pair_cached<4, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
+            case 5: jacobi_pair_cached<5, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
+            default: jacobi_pair_cached<6, G>(xi, xj, q, qx, gl, gmask, floor2, big, rec + slot); break;
           }
         } else {
           double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
@@ -208,9 +224,12 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
             cr = fma(u.x, v.x, fma(u.y, v.y, cr));
             ci = fma(u.y, v.x, fma(-u.x, v.y, ci));
           }
-          group_sum4<G>(a, b, cr, ci, gmask);
+          const double mine = group_reduce4<G>(a, b, cr, ci, gl, gmask);
+          if (gl < 4) reinterpret_cast<double*>(rec + slot)[owner_pos(gl)] = mine;
+          __syncwarp(gmask);
+          const PairSums tot = rec[slot];
           Rotation R;
-          if (make_rotation(a, b, cr, ci, floor2, big, R)) {
+          if (make_rotation(tot.a, tot.b, tot.cr, tot.ci, floor2, big, R)) {
             for (int c = gl; c < q; c += G) {
               const cplx u = xi[c], v = xj[c];
               const double vr = R.er * v.x - R.ei * v.y, vi = R.er * v.y + R.ei * v.x;
@@ -303,14 +322,34 @@ __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __
 //   the same decisions and build the same rotation) -> rotates its own columns.
 // Per-SM arithmetic drops ~C-fold for the sums and the updates; the rotation itself (three special-function chains) is
 // recomputed everywhere.  The price is one cluster barrier (~400 cycles) + 32 B x pairs x C of DSMEM traffic per step.
-struct __align__(16) PairSums { double a, b, cr, ci; };
 constexpr int CL_C = 4;     // CTAs per cluster
 constexpr int CL_G = 8;     // lanes per row pair
 
-template <int CPL>
+// The per-step exchange does not use the cluster barrier (its release fence costs ~900 cycles per step here): partial sums
+// travel as asynchronous DSMEM stores that complete a transaction count on the RECEIVER's mbarrier (st.async ...
+// mbarrier::complete_tx::bytes; SASS: STAS + SYNCS), and each CTA waits on its own mbarrier only.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_2f64(uint32_t remote_addr, double x, double y, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+               :: "r"(remote_addr), "d"(x), "d"(y), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spins = 0; !done && spins < (1 << 20); ++spins)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+
+template <int CPL, int G>
 __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
                                                            int n_slots, SmallArgs g) {
-  constexpr int C = CL_C, G = CL_G;
+  constexpr int C = CL_C;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -318,14 +357,17 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
   const bool mode_t = m > n;
   const int p = mode_t ? n : m, qx = mode_t ? m : n, q = mode_t ? m + n : n;
   const int ql = (q + C - 1) / C, c0 = rank * ql;                       // this CTA's column slice [c0, c0 + qn)
+  const int ld = ql | 1;                                                // odd row stride: rows start in different banks
   const int qn = max(0, min(ql, q - c0)), qxn = max(0, min(qn, qx - c0));     // qxn: local columns that are data (enter the Gram sums)
   const int pp = (p + 1) & ~1, npairs = pp / 2;
-  cplx* X = reinterpret_cast<cplx*>(sm_raw);                                    // p x ql
-  PairSums* part = reinterpret_cast<PairSums*>(sm_raw + sizeof(cplx) * (size_t)p * ql);   // [2][C][npairs]
-  double* s2p = reinterpret_cast<double*>(part + 2 * C * npairs);                // [C][p]
+  cplx* X = reinterpret_cast<cplx*>(sm_raw);                                    // p x ld
+  PairSums* part = reinterpret_cast<PairSums*>(sm_raw + sizeof(cplx) * (size_t)p * ld);   // [2][C][npairs]
+  PairSums* rec = part + 2 * C * npairs;                                        // [npairs] this CTA's own sums of the current step
+  double* s2p = reinterpret_cast<double*>(rec + npairs);                        // [C][p]
   double* s2 = s2p + C * p;                                                     // p
   int* idx = reinterpret_cast<int*>(s2 + p);                                    // p
   __shared__ double red[34];
+  __shared__ __align__(8) unsigned long long bar[2];                            // one mbarrier per exchange buffer
 
   cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* A = cb + g.A;
@@ -337,12 +379,12 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
   if (!mode_t) {
     for (int e = t; e < p * qn; e += nt) {
       const int r = e / qn, cl = e - r * qn;
-      X[r * ql + cl] = A[(long long)r * g.lda + c0 + cl];
+      X[r * ld + cl] = A[(long long)r * g.lda + c0 + cl];
     }
   } else {
     for (int e = t; e < p * qn; e += nt) {
       const int cl = e / p, r = e - cl * p, c = c0 + cl;                    // row r of X = column r of A, then row r of I
-      X[r * ql + cl] = c < m ? A[(long long)c * g.lda + r] : cmake(c - m == r ? 1.0 : 0.0, 0.0);
+      X[r * ld + cl] = c < m ? A[(long long)c * g.lda + r] : cmake(c - m == r ? 1.0 : 0.0, 0.0);
     }
   }
   double fro = 0.0;
@@ -351,17 +393,26 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
   const double floor2 = 1e-34 * fro2;
 
   const int slot = t / G, gl = t - slot * G;
-  const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
-  // where lane gl < C delivers this CTA's partial sums: CTA gl's copy of part[.][rank][slot]
-  PairSums* remote = cluster.map_shared_rank(part + rank * npairs + (slot < npairs ? slot : 0), gl < C ? gl : 0);
-  bool converged = p < 2;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  // where lane gl < C delivers this CTA's partial sums: CTA gl's copy of part[.][rank][slot], completing CTA gl's mbarrier
+  const uint32_t remote_part = map_to_rank(smem_u32(part + rank * npairs + (slot < npairs ? slot : 0)), gl < C ? gl : 0);
+  const uint32_t remote_bar = map_to_rank(smem_u32(&bar[0]), gl < C ? gl : 0);
+  const uint32_t bar0 = smem_u32(&bar[0]);
+  const uint32_t step_bytes = (uint32_t)(C * (p / 2) * sizeof(PairSums));   // p/2 real pairs per step, from each of the C CTAs
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  bool converged = p < 2, lost = false;
   int tick = 0;
+  uint32_t parity = 0;                              // bit k: phase parity of bar[k]
 #ifdef KBP_SMALL_DEBUG
   long long tstart = clock64();
-  long long ph[4] = {0, 0, 0, 0};
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
   cluster.sync();                                   // every CTA of the cluster is resident before the first remote store
-  for (int sweep = 0; sweep < SMALL_MAX_SWEEPS && !converged; ++sweep) {
+  for (int sweep = 0; sweep < SMALL_MAX_SWEEPS && !converged && !lost; ++sweep) {
     bool big = false;
     PairWalk walk;
     walk.start(pp, slot);
@@ -369,12 +420,17 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
 #ifdef KBP_SMALL_DEBUG
       const long long k0 = clock64();
 #endif
+      if (t == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar0 + 8 * tick), "r"(step_bytes) : "memory");
       int i, j;
       walk.get(step, i, j);
       const bool act = slot < npairs && j < p;
+#ifdef KBP_SMALL_DEBUG
+      const long long q0 = clock64();
+      long long q1 = q0, q2 = q0;
+#endif
       cplx u[CPL], v[CPL];
-      cplx* xi = X + i * ql;
-      cplx* xj = X + j * ql;
+      cplx* xi = X + i * ld;
+      cplx* xj = X + j * ld;
       if (act) {
         double a = 0.0, b = 0.0, cr = 0.0, ci = 0.0;
 #pragma unroll
@@ -389,17 +445,27 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
             ci = fma(u[k].y, v[k].x, fma(-u[k].x, v[k].y, ci));
           }
         }
-        group_sum4<G>(a, b, cr, ci, gmask);
+#ifdef KBP_SMALL_DEBUG
+        q1 = clock64() + (long long)(a * 0.0);
+#endif
+        const double mine = group_reduce4<G>(a, b, cr, ci, gl, gmask);
+#ifdef KBP_SMALL_DEBUG
+        q2 = clock64() + (long long)(mine * 0.0);
+#endif
+        if (gl < 4) reinterpret_cast<double*>(rec + slot)[owner_pos(gl)] = mine;
+        __syncwarp(gmask);
         if (gl < C) {
-          PairSums ps;
-          ps.a = a; ps.b = b; ps.cr = cr; ps.ci = ci;
-          remote[tick * C * npairs] = ps;
+          const PairSums ps = rec[slot];
+          const uint32_t dst = remote_part + (uint32_t)(tick * C * npairs * sizeof(PairSums));
+          st_async_2f64(dst, ps.a, ps.b, remote_bar + 8 * tick);
+          st_async_2f64(dst + 16, ps.cr, ps.ci, remote_bar + 8 * tick);
         }
       }
 #ifdef KBP_SMALL_DEBUG
       const long long k1 = clock64();
 #endif
-      cluster.sync();
+      if (!mbar_wait(bar0 + 8 * tick, (parity >> tick) & 1u)) lost = true;      // (never in a healthy run: bounded spin instead of a hang)
+      parity ^= 1u << tick;
 #ifdef KBP_SMALL_DEBUG
       const long long k2 = clock64();
 #endif
@@ -432,18 +498,20 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
 #ifdef KBP_SMALL_DEBUG
       const long long k4 = clock64();
       ph[0] += k1 - k0; ph[1] += k2 - k1; ph[2] += k3 - k2; ph[3] += k4 - k3;
+      ph[4] += q0 - k0; ph[5] += q1 - q0; ph[6] += q2 - q1; ph[7] += k1 - q2;
 #endif
     }
     converged = !__syncthreads_or(big ? 1 : 0);     // identical in every CTA: same totals, same decisions
+    lost = __syncthreads_or(lost ? 1 : 0) != 0;
 #ifdef KBP_SMALL_DEBUG
-    if (t == 0 && rank == 0) printf("[cluster %dx%d C %d G %d] sweep %d converged %d  cycles %lld  phases: dots %lld barrier %lld rotate %lld sync %lld\n", p, q, C, G, sweep, (int)converged, clock64() - tstart, ph[0], ph[1], ph[2], ph[3]);
+    if (t == 0 && rank == 0) printf("[cluster %dx%d C %d G %d] sweep %d converged %d  cycles %lld  phases: dots %lld barrier %lld rotate %lld sync %lld | expect+walk %lld load+fma %lld shuffles %lld send %lld\n", p, q, C, G, sweep, (int)converged, clock64() - tstart, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
 #endif
   }
 
   // ---- singular values: partial row norms -> every CTA, summed in rank order
   for (int i = w; i < p; i += nw) {
     double acc = 0.0;
-    const cplx* row = X + i * ql;
+    const cplx* row = X + i * ld;
     for (int cl = lane; cl < qxn; cl += 32) acc += cabs2(row[cl]);
     acc = warp_sum(acc);
     if (lane < C) *cluster.map_shared_rank(s2p + rank * p + i, lane) = acc;
@@ -475,7 +543,7 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
     for (int e = t; e < keep * qn; e += nt) {
       const int k = e / qn, cl = e - k * qn;
       const double sk2 = s2[idx[k]];
-      Vh[(long long)k * n + c0 + cl] = sk2 > floor2 ? cscale(X[idx[k] * ql + cl], rsqrt(sk2)) : cmake(0.0, 0.0);
+      Vh[(long long)k * n + c0 + cl] = sk2 > floor2 ? cscale(X[idx[k] * ld + cl], rsqrt(sk2)) : cmake(0.0, 0.0);
     }
     if (g.US >= 0) {
       // US = A Vh_k^H needs whole rows of Vh: publish them, then CTA r takes the rows r, r + C, ... of US
@@ -495,7 +563,7 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
   } else {
     for (int e = t; e < keep * qn; e += nt) {
       const int k = e / qn, cl = e - k * qn, c = c0 + cl;
-      const cplx x = X[idx[k] * ql + cl];
+      const cplx x = X[idx[k] * ld + cl];
       if (c < m) { if (g.US >= 0) US[(long long)c * keep + k] = cscale(x, scale); }
       else Vh[(long long)k * n + (c - m)] = s2[idx[k]] > floor2 ? cconj(x) : cmake(0.0, 0.0);
     }
@@ -504,15 +572,15 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
     double* sl = slots + (long long)blockIdx.y * n_slots;
     if (g.nr_bulk && g.slot_lognorm >= 0 && frob > 0.0) sl[g.slot_lognorm] += log(frob);
     if (g.slot_trunc >= 0 && fro2 > 0.0) sl[g.slot_trunc] += sqrt(disc / fro2);
-    if (!converged) sl[n_slots - 1] += 1.0;
+    if (!converged || lost) sl[n_slots - 1] += 1.0;
   }
 }
 
-template <int CPL>
+template <int CPL, int G>
 static cudaError_t launch_cluster(const Arena& a, const SmallArgs& g, int C, int threads, size_t smem) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(svd_cluster_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+    cudaFuncSetAttribute(svd_cluster_kernel<CPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -527,7 +595,7 @@ static cudaError_t launch_cluster(const Arena& a, const SmallArgs& g, int C, int
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, svd_cluster_kernel<CPL>, a.base, (long long)a.chain_stride, a.slots, a.n_slots, g);
+  return cudaLaunchKernelEx(&cfg, svd_cluster_kernel<CPL, G>, a.base, (long long)a.chain_stride, a.slots, a.n_slots, g);
 }
 
 void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
@@ -551,22 +619,19 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
   static const bool cluster_on = !(getenv("KBP_SMALL_CLUSTER") && atoi(getenv("KBP_SMALL_CLUSTER")) == 0);
   static const int cluster_minp = getenv("KBP_SMALL_CLUSTER_MINP") ? atoi(getenv("KBP_SMALL_CLUSTER_MINP")) : 48;
   if (cluster_on && p >= cluster_minp) {
-    const int C = CL_C, ql = (q + C - 1) / C, cpl = (ql + CL_G - 1) / CL_G;
-    if (cpl <= 6 && npairs * CL_G <= 1024) {
-      g.group = CL_G;
-      int threads = (npairs * CL_G + 31) / 32 * 32;
-      if (threads < 128) threads = 128;
-      const size_t smem = sizeof(double2) * (size_t)p * ql + sizeof(PairSums) * 2 * (size_t)C * npairs +
+    // (4 and 2 lanes per pair were measured slower: the per-lane FP64 work grows faster than the shuffles shrink)
+    const int C = CL_C, ql = (q + C - 1) / C, Gc = CL_G;
+    const int cpl = (ql + Gc - 1) / Gc;
+    if (cpl <= 6 && npairs * Gc <= 1024) {
+      g.group = Gc;
+      int threads = (npairs * Gc + 31) / 32 * 32;
+      if (threads < 64) threads = 64;
+      const size_t smem = sizeof(double2) * (size_t)p * (ql | 1) + sizeof(PairSums) * (2 * (size_t)C + 1) * npairs +
                           sizeof(double) * ((size_t)C * p + p) + sizeof(int) * (size_t)p + 64;
-      cudaError_t e = cudaSuccess;
-      switch (cpl) {
-        case 1: e = launch_cluster<1>(a, g, C, threads, smem); break;
-        case 2: e = launch_cluster<2>(a, g, C, threads, smem); break;
-        case 3: e = launch_cluster<3>(a, g, C, threads, smem); break;
-        case 4: e = launch_cluster<4>(a, g, C, threads, smem); break;
-        case 5: e = launch_cluster<5>(a, g, C, threads, smem); break;
-        default: e = launch_cluster<6>(a, g, C, threads, smem); break;
-      }
+      cudaError_t e = cudaErrorInvalidValue;
+#define KBP_CL(CP, GG) if (cpl == CP && Gc == GG) e = launch_cluster<CP, GG>(a, g, C, threads, smem)
+      KBP_CL(1, 8); KBP_CL(2, 8); KBP_CL(3, 8); KBP_CL(4, 8); KBP_CL(5, 8); KBP_CL(6, 8);
+#undef KBP_CL
       if (e == cudaSuccess) { ++*a.launches; return; }
       cudaGetLastError();                           // cluster launch refused: use the one-CTA kernel
     }

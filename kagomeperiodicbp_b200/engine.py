@@ -89,7 +89,7 @@ def svd_warm_elems(m: int, n: int, keep: int) -> int:
     Mirrors kbp_svd_warm_elems / tsvd_block in k_tsvd.cu."""
     p = min(m, n)
     q = n if m <= n else m + n
-    if p <= 128 and p * q * 16 + p * 12 + 64 <= 225 * 1024:
+    if p <= 128 and p * q * 16 + p * 12 + 16 + ((p + 1) // 2) * 32 + 64 <= 225 * 1024:
         return 0                                  # in-shared-memory Jacobi
     b = min(112, (keep * 25 // 10 + 7) // 8 * 8)
     if b < keep + 8 or b * 100 > p * 80:

@@ -442,6 +442,9 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
   static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
   static const int it_warm = getenv("KBP_TSVD_ITWARM") ? atoi(getenv("KBP_TSVD_ITWARM")) : 2;
   static const int it_step = getenv("KBP_TSVD_ITSTEP") ? atoi(getenv("KBP_TSVD_ITSTEP")) : 3;
+  // cold start: after `safe0` SAFE iterations the block is already ordered well enough (contamination of column j by a
+  // larger direction i has decayed as (s_j/s_i)^(2k), one fast step amplifies it by (s_i/s_j)^2) for the FAST form
+  static const int safe0 = getenv("KBP_TSVD_SAFE0") ? atoi(getenv("KBP_TSVD_SAFE0")) : 2;
   // a block narrower than 2.5 keep (shared-memory cap of the b x b kernels, e.g. D = 6: keep 72, b 112) converges more slowly:
   // more iterations are still far cheaper than the exact path on a (chi D^2)^2 matrix
   static const int it_max_env = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 0;
@@ -526,12 +529,15 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     auto it = a.sched->find(sched_key);
     if (it != a.sched->end()) first = it->second;
   }
+  bool allow_cold_fast = true;
   int done = 0, target = first;
   if (target < 1) target = 1;
   int checks = 0;
   while (true) {
     const bool rr_ordered = ordered;
+    bool cold_fast = false;
     if (replayed && checks == 0) {
+      cold_fast = tg->cold_fast;
       if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
       Qb = tg->Qb; f0 = tg->f0; f1 = tg->f1; f2 = tg->f2; done = tg->done;
       *a.launches += tg->launches;
@@ -540,7 +546,17 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     ++*a.launches;
     for (; done < target; ++done) {
       gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
-      if (!ordered) {
+      if (!ordered && allow_cold_fast && done >= safe0) {
+        if (!cold_fast) {                                             // pivots of the SAFE start say nothing about the FAST steps
+          tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
+          ++*a.launches;
+          cold_fast = true;
+        }
+        gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
+        cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f0
+        if (done + 1 == target) { cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat); replace_q(f1); }   // twice on the last one
+        else replace_q(f0);
+      } else if (!ordered) {
         cholqr_pass(a, f0, f1, Gp, Ri, Rs, m, b, stat);               // Y = orth(W)      -> f1
         gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                      // Z = A^H Y        -> f0
         cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f1
@@ -584,7 +600,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
       if (e1 == cudaSuccess && graph) e2 = cudaGraphInstantiate(&tg->exec, graph, 0);
       if (graph) cudaGraphDestroy(graph);
       if (e2 != cudaSuccess) { tg->exec = nullptr; tg->bad = true; cudaGetLastError(); return -1; }
-      tg->Qb = Qb; tg->f0 = f0; tg->f1 = f1; tg->f2 = f2; tg->done = done;
+      tg->Qb = Qb; tg->f0 = f0; tg->f1 = f1; tg->f2 = f2; tg->done = done; tg->cold_fast = cold_fast;
       tg->launches = *a.launches - launches_before;
       if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
       capturing = false;
@@ -601,10 +617,10 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
       if (df > maxdisc) maxdisc = df;
     }
     if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d%s%s] it %d resid %.3e s_k/s_1 %.3e min pivot %.3e disc %.3e\n", (long long)m, (long long)n,
-                       (long long)keep, b, is_warm ? " warm" : "", rr_ordered ? " fast" : "", done, worst, minratio, minpiv, maxdisc);
+                       (long long)keep, b, is_warm ? " warm" : "", rr_ordered ? " fast" : (cold_fast ? " cold-fast" : ""), done, worst, minratio, minpiv, maxdisc);
     // a spectrum that collapses inside the kept part: fine if nothing measurable is discarded (rank <= keep), else exact
     // path.  A fast round whose Cholesky pivots were small says nothing either way: it is redone with safe iterations.
-    const bool trusted = !rr_ordered || minpiv >= TSVD_PIVOT_TRUST;
+    const bool trusted = !(rr_ordered || cold_fast) || minpiv >= TSVD_PIVOT_TRUST;
     const bool collapse = trusted && minratio < TSVD_MIN_RATIO && maxdisc > 1e-24;
     ++checks;
     if (!collapse && trusted && worst <= TSVD_RES_TOL) {
@@ -626,6 +642,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     gemm(a, f2, Qb, Vbs, n, b, b, OP_N, OP_C);
     replace_q(f2);
     ordered = trusted;
+    if (!trusted) allow_cold_fast = false;
     target = done + (done < 12 ? it_step : 2 * it_step);
     if (target > it_max) target = it_max;
   }

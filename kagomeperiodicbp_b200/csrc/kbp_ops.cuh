@@ -16,7 +16,7 @@ struct TsvdGraph {
   long long Qb = 0, f0 = 0, f1 = 0, f2 = 0;
   int done = 0, seen = 0;
   long long launches = 0;
-  bool bad = false;
+  bool bad = false, cold_fast = false;
 };
 
 struct Arena {

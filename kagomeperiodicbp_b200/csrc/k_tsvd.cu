@@ -571,7 +571,8 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     // ---- Rayleigh-Ritz on span(Q)
     gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q -> f0
     int64_t Rsmall;
-    if (rr_ordered) {
+    static const bool rr_single = !(getenv("KBP_TSVD_RR_SINGLE") && atoi(getenv("KBP_TSVD_RR_SINGLE")) == 0);
+    if (rr_ordered || (cold_fast && rr_single)) {
       cholqr_pass(a, f0, -1, Gp, Ri, R1, m, b, stat);                 // W = Y R1
       Rsmall = R1;
     } else {

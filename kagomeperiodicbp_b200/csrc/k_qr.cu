@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ 
 
 void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   if (m == 0 || n == 0) return;
+  if (qr_cluster(a, A, Q, R, m, n)) return;                // shared-memory resident, rows over a cluster (k_qr_cluster.cu)
   qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n);
   ++*a.launches;
 }

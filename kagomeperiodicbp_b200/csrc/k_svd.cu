@@ -457,6 +457,8 @@ int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work
     }
   }
   ++a.counters[4];
+  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[kbp svd %lldx%lld keep %lld] block-Jacobi path\n", (long long)m, (long long)n, (long long)keep);
   const int r = svd_truncate_jacobi(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
   phase_fix(a, Vh, US, m, n, keep, 1);
   return r;

@@ -58,6 +58,8 @@ void permute(const Arena& a, int64_t dst, int64_t src, int conj, int ndim, const
 void gemm(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB);
 // A(m x n) = Q(m x r) R(r x n), r = min(m, n), Q^H Q = I.  work: m*n + n elements
 void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);
+// the same on a thread-block cluster with the matrix in distributed shared memory; false: shape not handled, nothing launched
+bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int64_t n);
 // rank-`keep` truncated SVD of A(m x n):  US(m x keep) = U_k diag(s_k) [ / ||A||_F if nr_bulk ],  Vh(keep x n).
 // slot_lognorm += ln ||A||_F (if nr_bulk); slot_trunc += sqrt(sum_discarded s^2 / sum s^2).
 // work: see svd_work_elems().  Returns the number of Jacobi sweeps used (max over chains), <0 on failure.

@@ -68,7 +68,8 @@ def test_tensordot_conj(eng):
     assert np.allclose(res[0][0], e, atol=1e-13)
 
 
-@pytest.mark.parametrize("m,n", [(5, 3), (3, 5), (16, 16), (162, 18), (18, 162), (512, 32), (64, 64), (1, 4), (4, 1)])
+@pytest.mark.parametrize("m,n", [(5, 3), (3, 5), (16, 16), (162, 18), (18, 162), (512, 32), (64, 64), (1, 4), (4, 1), (256, 32), (768, 48),
+                                 (243, 27), (256, 16), (130, 7), (1024, 40), (1100, 16), (96, 200)])
 def test_qr(eng, m, n):
     batch = [[rnd(m, n)] for _ in range(3)]
     # make one of them rank deficient
@@ -82,6 +83,19 @@ def test_qr(eng, m, n):
         assert np.linalg.norm(q @ r - a) <= 1e-13 * max(1.0, np.linalg.norm(a))
         assert np.linalg.norm(q.conj().T @ q - np.eye(k)) <= 1e-13 * k
         assert np.allclose(np.tril(r, -1), 0)
+
+
+def test_qr_tiny_scale(eng):
+    """columns at 1e-150 (rows the truncation emptied) must not underflow in the norms (bmpslib keeps such tensors alive)"""
+    for m, n in [(512, 32), (64, 16)]:
+        a = rnd(m, n)
+        a[:, n // 2:] *= 1e-150
+        res, _ = run(eng, lambda p, t: list(p.qr(t[0])), [[a]])
+        q, r = res[0]
+        assert np.linalg.norm(q.conj().T @ q - np.eye(n)) <= 1e-13 * n
+        d = q @ r - a
+        assert np.linalg.norm(d[:, :n // 2]) <= 1e-13 * np.linalg.norm(a)
+        assert np.linalg.norm(d[:, n // 2:]) <= 1e-13 * np.linalg.norm(a[:, n // 2:])
 
 
 def test_lq(eng):

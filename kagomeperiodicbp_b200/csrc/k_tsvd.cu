@@ -214,14 +214,26 @@ __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long
                                                    long long Out_, int rows, int b) {
   extern __shared__ __align__(16) unsigned char tr_raw[];
   const int nblk = (b + CNB - 1) / CNB;
-  cplx* Xs = reinterpret_cast<cplx*>(tr_raw);                     // nblk x 16 x 16
+  cplx* Xs = reinterpret_cast<cplx*>(tr_raw);                     // nblk x 16 x 16: inverses of the diagonal blocks
   cplx* xs = Xs + (size_t)nblk * CNB * CNB;                       // 32 x (b + 1): solved entries of the CTA's rows
   cplx* tmp = xs + 32 * (size_t)(b + 1);                          // 32 x 17
+  cplx* Rs = tmp + 32 * 17;                                       // the blocks of R above the diagonal blocks, packed per block column
   cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* R = cb + R_;
   const cplx* Xd = cb + Xd_;
   const int t = threadIdx.x;
   for (int e = t; e < nblk * CNB * CNB; e += blockDim.x) Xs[e] = Xd[e];
+  // R is shared by every row: one coalesced pass through L2 instead of a dependent L2 load per inner-loop step
+  // (block column pb holds rows [0, 16 pb) x columns [16 pb, 16 pb + 16) at offset 256 pb (pb - 1) / 2)
+  {
+    const int total = CNB * CNB * (nblk * (nblk - 1) / 2);
+    for (int e = t; e < total; e += blockDim.x) {
+      int pb = 1, off = 0;
+      while (e >= off + CNB * CNB * pb) { off += CNB * CNB * pb; ++pb; }
+      const int loc = e - off, i = loc >> 4, c = loc & 15, col = pb * CNB + c;
+      Rs[e] = col < b ? __ldg(R + (long long)i * b + col) : cmake(0.0, 0.0);
+    }
+  }
   __syncthreads();
   const int r = t >> 4, c = t & 15;
   const int row = blockIdx.x * 32 + r;
@@ -233,11 +245,17 @@ __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long
   for (int pb = 0; pb < nblk; ++pb) {
     const int p0 = pb * CNB, col = p0 + c;
     cplx acc = (ok && col < b) ? y[col] : cmake(0.0, 0.0);
-    if (col < b)
-      for (int i = 0; i < p0; ++i) {
-        const cplx v = cmul(xr[i], __ldg(R + i * b + col));       // R (b x b) stays in L2: 16 consecutive columns per row of threads
-        acc.x -= v.x; acc.y -= v.y;
+    {
+      const cplx* rc = Rs + CNB * CNB * (pb * (pb - 1) / 2) + c;  // column c of block column pb
+      cplx acc2 = cmake(0.0, 0.0);
+      int i = 0;
+      for (; i + 1 < p0; i += 2) {                                 // two independent chains
+        const cplx v0 = cmul(xr[i], rc[i * CNB]), v1 = cmul(xr[i + 1], rc[(i + 1) * CNB]);
+        acc.x -= v0.x; acc.y -= v0.y;
+        acc2.x -= v1.x; acc2.y -= v1.y;
       }
+      acc.x += acc2.x; acc.y += acc2.y;
+    }
     tr[c] = acc;
     __syncwarp();
     cplx x = cmake(0.0, 0.0);
@@ -414,7 +432,8 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
   ++*a.launches;
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
-    const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17) + 32;
+    const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17 +
+                                            (size_t)CNB * CNB * (nblk * (nblk - 1) / 2)) + 32;
     trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b);
     ++*a.launches;
   }

@@ -18,11 +18,60 @@
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
 
+#include <mutex>
+#include <vector>
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 namespace kbp {
+
+// ---- developer aid (KBP_TSVD_PROF=1, with KBP_GRAPHS=0): in-situ time of each kernel category of the subspace-iteration
+// SVD, measured with events on the chain's own stream; totals over all chains are printed when the process exits.
+namespace {
+struct CatProf {
+  bool on = getenv("KBP_TSVD_PROF") != nullptr;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cats;
+  size_t used = 0;
+  void mark(cudaStream_t st, int cat) {
+    if (!on) return;
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    cudaEventRecord(pool[used++], st);
+    cats.push_back(cat);
+  }
+  void flush();
+};
+const char* const CAT_NAMES[8] = {"gemm A Q / A^H W", "gram gemm", "chol", "trsm", "small svd", "rayleigh-ritz gemms + phase", "checks + misc", "start"};
+std::mutex g_prof_mu;
+double g_prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+long long g_prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+void CatProf::flush() {
+  if (!on || used < 2) { used = 0; cats.clear(); return; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  static bool registered = false;
+  if (!registered) {
+    registered = true;
+    atexit([] {
+      double tot = 0;
+      for (int c = 0; c < 8; ++c) tot += g_prof_ms[c];
+      for (int c = 0; c < 7; ++c)
+        fprintf(stderr, "[kbp tsvd prof] %-28s %9.2f ms  %5.1f %%  (%lld spans, %.1f us each)\n", CAT_NAMES[c], g_prof_ms[c], 100.0 * g_prof_ms[c] / (tot > 0 ? tot : 1),
+                g_prof_n[c], g_prof_n[c] ? 1e3 * g_prof_ms[c] / g_prof_n[c] : 0.0);
+    });
+  }
+  for (size_t k = 1; k < used; ++k) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, pool[k - 1], pool[k]) == cudaSuccess) { g_prof_ms[cats[k]] += ms; ++g_prof_n[cats[k]]; }
+  }
+  used = 0;
+  cats.clear();
+}
+thread_local CatProf t_prof;
+}  // namespace
+#define PM(cat) t_prof.mark(a.stream, cat)
+
 
 constexpr int TSVD_BMAX = 112;            // b x b complex must fit one CTA's shared memory (chol + small SVD)
 constexpr double TSVD_RES_TOL = 2e-13;
@@ -78,27 +127,50 @@ __global__ void tsvd_randq_kernel(cplx* __restrict__ base, long long chain_strid
 // columns of pivot/diagonal.  Outputs: R (b x b, upper, row-major), Dinv (b entries, 1/R_jj in .x).
 constexpr int CNB = 16;
 
-__global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
+__global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
                                                     long long Dinv_, long long Xd_, int b, double* __restrict__ stat) {
   extern __shared__ __align__(16) unsigned char ch_raw[];
   const int ld = b + 1;                                            // odd row stride: the 16 rows of a panel fall into different banks
   cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x ld
   double* diag0 = reinterpret_cast<double*>(S + (size_t)b * ld);   // original diagonal
   double* dinv = diag0 + b;                                        // 1 / R_jj (0 for dropped columns)
+  double* piv = dinv + b;                                          // pivot of each column (-1: dropped)
   __shared__ double sh_min;
   __shared__ cplx rowbuf[4 * CNB];                                 // [parity][row line | column line]
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
   const cplx* G = cb + G_;
   const int t = threadIdx.x, nt = blockDim.x;
-  for (int e = t; e < b * b; e += nt) {
-    cplx v = G[e];
-    for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, G[(long long)sp * b * b + e]);
-    S[(e / b) * ld + e % b] = v;
+#ifdef KBP_CHOL_TIMING
+  long long tk[6] = {0, 0, 0, 0, 0, 0};
+  long long tq = clock64();
+#define CHTICK(k) { const long long now_ = clock64(); tk[k] += now_ - tq; tq = now_; }
+#else
+#define CHTICK(k)
+#endif
+  {
+    // sum of the split-K partial Gram matrices; (row, column) from the warp / lane, no integer division, all partials of
+    // several rows in flight at once
+    const int lane = t & 31, w = t >> 5, nw = nt >> 5;
+    const long long bb = (long long)b * b;
+    for (int r = w; r < b; r += nw) {
+      for (int c = lane; c < b; c += 32) {
+        const cplx* gp = G + (long long)r * b + c;
+        cplx v = gp[0];
+        if (nsplit == 4) {
+          const cplx v1 = gp[bb], v2 = gp[2 * bb], v3 = gp[3 * bb];
+          v = cadd(cadd(v, v1), cadd(v2, v3));
+        } else {
+          for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, gp[(long long)sp * bb]);
+        }
+        S[r * ld + c] = v;
+      }
+    }
   }
   __syncthreads();
   for (int i = t; i < b; i += nt) diag0[i] = S[i * ld + i].x;
   if (t == 0) sh_min = 1.0;
   __syncthreads();
+  CHTICK(0)
 
   for (int p0 = 0; p0 < b; p0 += CNB) {
     const int p1 = p0 + CNB < b ? p0 + CNB : b, pw = p1 - p0;
@@ -108,7 +180,6 @@ __global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, lon
       const bool in = row < pw && col < pw;
       cplx v = in ? S[(p0 + row) * ld + p0 + col] : cmake(row == col ? 1.0 : 0.0, 0.0);
       if (col < row) v = cconj(in ? S[(p0 + col) * ld + p0 + row] : cmake(0.0, 0.0));   // Hermitian: fill the lower part
-      double mn = 1.0;
       for (int j = 0; j < CNB; ++j) {
         cplx* rb = rowbuf + (j & 1) * 2 * CNB;
         cplx* cbuf = rb + CNB;
@@ -119,7 +190,7 @@ __global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, lon
         const double d0 = j < pw ? diag0[p0 + j] : 1.0;
         const bool live = d0 > 0.0 && d > TSVD_PIVOT_DEAD * d0;      // NaN -> dropped
         const double ip = live ? rsqrt(d) : 0.0;
-        if (t == 0 && live && j < pw) mn = fmin(mn, d * __drcp_rn(d0));
+        if (t == 0 && j < pw) piv[p0 + j] = live ? d : -1.0;
         const cplx srj = cbuf[row], sju = rb[col];                   // S[row][j], S[j][col]
         const double ip2 = ip * ip;
         const double vx = (srj.x * sju.x - srj.y * sju.y) * ip2, vy = (srj.x * sju.y + srj.y * sju.x) * ip2;
@@ -134,76 +205,114 @@ __global__ void __launch_bounds__(1024) chol_kernel(cplx* __restrict__ base, lon
         v = cmake(nx, ny);
         if (t == 0 && j < pw) dinv[p0 + j] = ip;
       }
-      if (t == 0) sh_min = fmin(sh_min, mn);
       if (in && col >= row) S[(p0 + row) * ld + p0 + col] = v;       // R (upper)
     }
     __syncthreads();
+    CHTICK(1)
     const int rem = b - p1;
     if (rem > 0) {
       // ---- phase B: R[r][l] = (S[r][l] - sum_{r' < r} conj(R[r'][r]) R[r'][l]) / R[r][r],  l >= p1
-      if (t < rem) {
-        const int l = p1 + t;
-        cplx colv[CNB];
+      // right-looking forward substitution, 16 lanes per column l (lane r owns row r of the panel): in step k lane k's value is
+      // final, goes to the other lanes by a half-warp shuffle, and every later row takes its term
+      for (int cb0 = 0; cb0 < rem; cb0 += nt >> 4) {
+        const int lc = cb0 + (t >> 4), r = t & 15;
+        const bool valid = lc < rem && r < pw;
+        const int l = p1 + (lc < rem ? lc : 0);
+        cplx acc = valid ? S[(p0 + r) * ld + l] : cmake(0.0, 0.0);
+        const double dv = r < pw ? dinv[p0 + r] : 0.0;
 #pragma unroll
-        for (int r = 0; r < CNB; ++r) {
-          cplx acc = cmake(0.0, 0.0);
-          if (r < pw) {
-            acc = S[(p0 + r) * ld + l];
-#pragma unroll
-            for (int rp = 0; rp < r; ++rp) {
-              const cplx v = ccmul(S[(p0 + rp) * ld + p0 + r], colv[rp]);
+        for (int k = 0; k < CNB; ++k) {
+          if (k < pw) {
+            cplx x = cscale(acc, dv);
+            x.x = __shfl_sync(0xffffffffu, x.x, k, 16);
+            x.y = __shfl_sync(0xffffffffu, x.y, k, 16);
+            if (r == k) acc = x;
+            if (r > k && r < pw) {
+              const cplx v = ccmul(S[(p0 + k) * ld + p0 + r], x);
               acc.x -= v.x; acc.y -= v.y;
             }
-            acc = cscale(acc, dinv[p0 + r]);
-            S[(p0 + r) * ld + l] = acc;
           }
-          colv[r] = acc;
         }
+        if (valid) S[(p0 + r) * ld + l] = acc;
       }
       __syncthreads();
+      CHTICK(2)
       // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
-      for (int e = t; e < rem * rem; e += nt) {
-        const int i = p1 + e / rem, l = p1 + e % rem;
-        if (l >= i) {
-          cplx x = S[i * ld + l];
-          for (int r = p0; r < p1; ++r) {
-            const cplx v = ccmul(S[r * ld + i], S[r * ld + l]);
-            x.x -= v.x; x.y -= v.y;
-          }
-          if (l == i) x.y = 0.0;
-          S[i * ld + l] = x;
+      // upper triangle only, folded into a (rem + 1) x ceil(rem / 2) rectangle: row rr carries matrix row rr (rem - rr entries)
+      // followed by matrix row rem - 1 - rr (rr + 1 entries)
+      for (int e = t; e < (rem + 1) * ((rem + 1) / 2); e += nt) {
+        const int rr = e / (rem + 1), cc = e - rr * (rem + 1);
+        int ii, ll;
+        if (cc < rem - rr) { ii = rr; ll = rr + cc; }
+        else { ii = rem - 1 - rr; ll = ii + (cc - (rem - rr)); }
+        if (cc >= rem - rr && ii == rr) continue;                  // odd rem: the middle row is listed once
+        const int i = p1 + ii, l = p1 + ll;
+        cplx x = S[i * ld + l], x2 = cmake(0.0, 0.0);
+        for (int r = p0; r + 1 < p1; r += 2) {
+          const cplx v = ccmul(S[r * ld + i], S[r * ld + l]), v2 = ccmul(S[(r + 1) * ld + i], S[(r + 1) * ld + l]);
+          x.x -= v.x; x.y -= v.y;
+          x2.x -= v2.x; x2.y -= v2.y;
         }
+        if (pw & 1) {
+          const cplx v = ccmul(S[(p1 - 1) * ld + i], S[(p1 - 1) * ld + l]);
+          x.x -= v.x; x.y -= v.y;
+        }
+        x.x += x2.x; x.y += x2.y;
+        if (l == i) x.y = 0.0;
+        S[i * ld + l] = x;
       }
       __syncthreads();
+      CHTICK(3)
     }
   }
   cplx* R = cb + R_;
-  for (int e = t; e < b * b; e += nt) R[e] = (e % b >= e / b) ? S[(e / b) * ld + e % b] : cmake(0.0, 0.0);
+  for (int r = t >> 5; r < b; r += nt >> 5)
+    for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
   cplx* Dv = cb + Dinv_;
   for (int i = t; i < b; i += nt) Dv[i] = cmake(dinv[i], 0.0);
-  // inverses of the 16 x 16 diagonal blocks (what the blocked triangular solve multiplies by), all panels in parallel, off
-  // the factorisation's critical path: 256 threads per panel, thread (l, r) holds x_rl, x_il = -dinv_i sum_{r=i+1..l} R[i][r] x_rl
-  // reduced over the 16 lanes of a half warp -- no block barrier
+  // inverses of the 16 x 16 diagonal blocks (what the blocked triangular solve multiplies by), all panels in parallel
   cplx* Xd = cb + Xd_;
   const int nblk = (b + CNB - 1) / CNB;
-  for (int pb = t >> 8; pb < nblk; pb += nt >> 8) {
+  // thread (panel, column l): back substitution up column l of X = R_pp^{-1}, right-looking (x_il = -dinv_i sum_{r > i} R[i][r] x_rl):
+  // a 16-step dependent chain per thread, all panels and columns in parallel
+  for (int e = t; e < nblk * CNB; e += nt) {
+    const int pb = e / CNB, l = e - pb * CNB;
     const int p0 = pb * CNB, pw = (p0 + CNB < b ? CNB : b - p0);
-    const int l = (t >> 4) & 15, rr = t & 15;
-    const bool act = l < pw && rr < pw;
-    cplx x = (act && rr == l) ? cmake(dinv[p0 + l], 0.0) : cmake(0.0, 0.0);
-    for (int i = CNB - 2; i >= 0; --i) {
-      cplx term = cmake(0.0, 0.0);
-      if (act && i < pw && rr > i && rr <= l) term = cmul(S[(p0 + i) * ld + p0 + rr], x);
+    cplx acc[CNB];
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        term.x += __shfl_xor_sync(0xffffffffu, term.x, o);
-        term.y += __shfl_xor_sync(0xffffffffu, term.y, o);
+    for (int i = 0; i < CNB; ++i) acc[i] = cmake(0.0, 0.0);
+    cplx* Xp = Xd + pb * CNB * CNB;
+    if (l < pw) {
+#pragma unroll
+      for (int i = CNB - 1; i >= 0; --i) {
+        if (i <= l) {
+          const cplx x = i == l ? cmake(dinv[p0 + l], 0.0) : cscale(acc[i], -dinv[p0 + i]);
+          Xp[i * CNB + l] = x;
+#pragma unroll
+          for (int i2 = 0; i2 < CNB; ++i2) {
+            if (i2 < i) acc[i2] = cfma(S[(p0 + i2) * ld + p0 + i], x, acc[i2]);
+          }
+        } else {
+          Xp[i * CNB + l] = cmake(0.0, 0.0);
+        }
       }
-      if (act && rr == i && i < l) x = cscale(term, -dinv[p0 + i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CNB; ++i) Xp[i * CNB + l] = cmake(0.0, 0.0);
     }
-    Xd[pb * CNB * CNB + rr * CNB + l] = (act && rr <= l) ? x : cmake(0.0, 0.0);     // X[rr][l]
   }
-  if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], sh_min);
+  CHTICK(4)
+#ifdef KBP_CHOL_TIMING
+  if (t == 0 && blockIdx.x == 0) printf("[chol b=%d] load %lld  A %lld  B %lld  C %lld  tail %lld cycles\n", b, tk[0], tk[1], tk[2], tk[3], tk[4]);
+#endif
+  if (t < 32) {                                                    // smallest pivot / diagonal over the live columns
+    double mn = 1.0;
+    for (int i = t; i < b; i += 32)
+      if (piv[i] > 0.0) mn = fmin(mn, piv[i] / diag0[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], mn);
+  }
 }
 
 // Out (rows x b) = Y R^{-1} for upper-triangular R by block forward substitution over the 16-column panels:
@@ -426,16 +535,19 @@ constexpr int GRAM_SPLIT = 4;
 static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat) {
   const int split = rows >= 256 ? GRAM_SPLIT : 1;
   gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
-  const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 2 * sizeof(double) * (size_t)b + 32;
+  PM(1);
+  const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 3 * sizeof(double) * (size_t)b + 32;
   const int64_t Xd = Dinv + b;                                     // diagonal-block inverses behind the 1/diagonal entries
-  chol_kernel<<<a.nb, 1024, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat);
+  chol_kernel<<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat);
   ++*a.launches;
+  PM(2);
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
     const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17 +
                                             (size_t)CNB * CNB * (nblk * (nblk - 1) / 2)) + 32;
     trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b);
     ++*a.launches;
+    PM(3);
   }
   return T;
 }
@@ -520,6 +632,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     }
   }
   const int64_t launches_before = *a.launches;
+  PM(7);
   if (ordered) {
     Qb = warm;                       // Ritz basis of the previous run of this op (n x b, orthonormal columns); read only
   } else {
@@ -565,6 +678,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     ++*a.launches;
     for (; done < target; ++done) {
       gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
+      PM(0);
       if (!ordered && allow_cold_fast && done >= safe0) {
         if (!cold_fast) {                                             // pivots of the SAFE start say nothing about the FAST steps
           tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
@@ -572,23 +686,27 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
           cold_fast = true;
         }
         gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
+        PM(0);
         cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f0
         if (done + 1 == target) { cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat); replace_q(f1); }   // twice on the last one
         else replace_q(f0);
       } else if (!ordered) {
         cholqr_pass(a, f0, f1, Gp, Ri, Rs, m, b, stat);               // Y = orth(W)      -> f1
         gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                      // Z = A^H Y        -> f0
+        PM(0);
         cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f1
         if (done + 1 == target) { cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat); replace_q(f0); }   // twice on the last one
         else replace_q(f1);
       } else {
         gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
+        PM(0);
         cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // Q = orth(Z)      -> f0
         replace_q(f0);
       }
     }
     // ---- Rayleigh-Ritz on span(Q)
     gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q -> f0
+    PM(0);
     int64_t Rsmall;
     static const bool rr_single = !(getenv("KBP_TSVD_RR_SINGLE") && atoi(getenv("KBP_TSVD_RR_SINGLE")) == 0);
     if (rr_ordered || (cold_fast && rr_single)) {
@@ -598,9 +716,11 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
       cholqr_pass(a, f0, f1, Gp, Ri, R1, m, b, stat);
       cholqr_pass(a, f1, -1, Gp, Ri, R2, m, b, stat);
       gemm(a, Rm, R2, R1, b, b, b, OP_N, OP_N);                       // W = Y (R2 R1)
+      PM(5);
       Rsmall = Rm;
     }
     svd_small(a, Rsmall, b, -1, Vbs, b, b, b, 0, -1, -1);             // Vbs = Vb^H (b x b), rows by decreasing singular value
+    PM(4);
     gemm(a, Vh, Vbs, Qb, keep, n, b, OP_N, OP_C);                     // Vh = Vb_k^H Q^H
     phase_fix(a, Vh, US, m, n, keep, 0);                              // canonical gauge of the kept bond
     gemm(a, US, A, Vh, m, keep, n, OP_N, OP_C);                       // US = A Vh^H
@@ -608,11 +728,13 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     gemm(a, Tk, f0, Vh, keep, keep, n, OP_N, OP_C);                   // T = C Vh^H
     gemm(a, f1, Tk, Vh, keep, n, keep, OP_N, OP_N);                   // TV = T Vh         -> f1
     gemm(a, Pb, US, Vh, m, n, keep, OP_N, OP_N);                      // P = US Vh
+    PM(5);
     tsvd_check1_kernel<<<dim3(NPART, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, f0, f1, A, Pb, (int)m, (int)n, (int)keep, part);
     tsvd_check2_kernel<<<a.nb, 128, 0, a.stream>>>(a.base, a.chain_stride, Tk, (int)keep, part, resid, ratio, discf, norms);
     *a.launches += 2;
     // one host round trip: [stat | resid | ratio | discfrac] are contiguous in svd_off
     cudaMemcpyAsync(a.svd_off_host, a.svd_off, sizeof(double) * 4 * a.nb, cudaMemcpyDeviceToHost, a.stream);
+    PM(6);
     if (capturing && checks == 0) {
       cudaGraph_t graph = nullptr;
       const cudaError_t e1 = cudaStreamEndCapture(a.stream, &graph);
@@ -627,6 +749,8 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     }
     }
     if (stream_wait(a) != cudaSuccess) return -1;
+    t_prof.flush();
+    PM(7);
     double worst = 0.0, minpiv = 1.0, minratio = 1.0, maxdisc = 0.0;
     for (int c = 0; c < a.nb; ++c) {
       const double pv = a.svd_off_host[c], rs = a.svd_off_host[a.nb + c], ra = a.svd_off_host[2 * a.nb + c], df = a.svd_off_host[3 * a.nb + c];
@@ -660,6 +784,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
     }
     // continue from the Ritz basis Q Vb (ordered) -- unless the fast path just proved untrustworthy
     gemm(a, f2, Qb, Vbs, n, b, b, OP_N, OP_C);
+    PM(5);
     replace_q(f2);
     ordered = trusted;
     if (!trusted) allow_cold_fast = false;

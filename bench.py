@@ -376,12 +376,13 @@ def main():
         share = svd_ms / max(1e-9, float(ms.sum()))
         achieved = svd_flops / (ms_step * 1e-3 * share) / 1e12
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                            # dram__bytes_read.sum + dram__bytes_write.sum per launch of the three kernels of the family, from the
-                            # `ncu --set full` capture summarised in profiles/r01_ncu_full_tsvd_kernels.csv and r01_SUMMARY.md
-                            # (cold L2; in the running step the operands are L2 resident: the family is not HBM bound)
-                            "traffic": 212480, "traffic_detail_bytes_per_launch": {"svd_small_kernel": 212480, "chol_inv_kernel": 465408,
+                            # dram__bytes_read.sum + dram__bytes_write.sum per launch, from `ncu --set full` captures summarised under
+                            # profiles/ (r01_ncu_full_chol_kernel_v2.csv for the current Cholesky kernel, r01_ncu_full_tsvd_kernels.csv
+                            # for the others; cold L2 -- in the running step the operands are L2 resident: the family is not HBM bound)
+                            "traffic": 479744, "traffic_detail_bytes_per_launch": {"chol_kernel": 479744, "svd_small_kernel (one CTA)": 212480,
                                                                                    "zgemm_dmma_kernel<32,32>": 780544},
-                            "kernel": "truncated-SVD family (zgemm_dmma_kernel + chol_inv_kernel + svd_small_kernel subspace iteration; svd_round_kernel fallback)",
+                            "kernel": "truncated-SVD family: subspace iteration = zgemm_dmma_kernel + chol_kernel + trsm_kernel per iteration, "
+                                      "svd_cluster_kernel / svd_small_kernel Rayleigh-Ritz (svd_round_kernel: exact fallback)",
                             "peak_source": "cuBLAS DGEMM 4096^3 FP64 measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
                             "algorithmic_flops_per_step": svd_flops, "svd_share_of_op_time": share,
                             "all_ops_algorithmic_flops_per_step": total_flops,

@@ -224,6 +224,11 @@ def main():
     from kagomeperiodicbp_b200.lattice import BLOCK_SIDES_CCW
     from kagomeperiodicbp_b200.runtime import get_engine
 
+    # stdout carries the ONE JSON line and nothing else: libraries that print there (NCCL's version banner when NCCL_DEBUG is
+    # set on the box) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -417,7 +422,8 @@ def main():
             line["cpu_baseline"] = cpu_sample(a, cells[0], msgs_list[0], a.cpu_budget_s)
         if world == 1 and a.ite_steps > 0:
             line["ite"] = ite_metric(a, cells[0], msgs_list[0], cfg, line.get("cpu_baseline"))
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -48,6 +48,11 @@ class MPS:
         self.nr_exp = int(e)
         self.nr_mantissa = 10.0 ** (l10 - e)
 
+    def reduceDiter(self, maxD, nr_bulk=False, max_iter=10, err=1e-6):
+        """QR-only iterative compression on the device, in place (src/libs/bmpslib.py:989-1364; see reduce_iter.py)."""
+        from . import reduce_iter
+        reduce_iter.reduceDiter(reduce_iter.backend(), self, maxD, nr_bulk=nr_bulk, max_iter=max_iter, err=err)
+
     def mps_shape(self) -> str:
         return " ".join(f"A_{i}{tuple(a.shape)}" for i, a in enumerate(self.A))
 

@@ -150,6 +150,16 @@ def test_cabi_library_exports_every_declared_symbol():
     from kagomeperiodicbp_b200.engine import svd_work_elems
     for m, n in [(512, 512), (256, 512), (162, 81), (5, 3)]:
         assert lib.kbp_svd_work_elems(m, n) == svd_work_elems(m, n)
+    # the Python mirrors that size program buffers must follow the library's rules (small-kernel fit, block width)
+    lib.kbp_svd_warm_elems.restype = ctypes.c_int64
+    lib.kbp_svd_warm_elems.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64]
+    lib.kbp_qr_work_elems.restype = ctypes.c_int64
+    lib.kbp_qr_work_elems.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    from kagomeperiodicbp_b200.engine import qr_work_elems, svd_warm_elems
+    for m, n, k in [(512, 512, 32), (256, 512, 32), (162, 162, 18), (81, 162, 18), (162, 81, 18), (84, 162, 18), (128, 110, 32), (129, 110, 32),
+                    (48, 512, 32), (2592, 2592, 72), (16, 32, 8), (100, 37, 37), (1296, 648, 72)]:
+        assert lib.kbp_svd_warm_elems(m, n, k) == svd_warm_elems(m, n, k), (m, n, k)
+        assert lib.kbp_qr_work_elems(m, n) == qr_work_elems(m, n)
 
 
 def test_no_cpu_fallback_without_device():

@@ -617,7 +617,7 @@ int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int
   // The first round of a cold start (pseudo-random block, a fixed number of iterations, Rayleigh-Ritz, copy of the flags) is
   // a constant launch sequence for a given op of a given program: captured into a CUDA graph on its second execution and
   // replayed afterwards (~70 launches -> one).  Everything that depends on the flags stays on the plain path.
-  static const bool graphs_on = !(getenv("KBP_GRAPHS") && atoi(getenv("KBP_GRAPHS")) == 0);
+  static const bool graphs_on = graphs_enabled();
   TsvdGraph* tg = nullptr;
   bool replayed = false, capturing = false;
   if (graphs_on && !is_warm && !debug && a.tsvd_graphs) {

@@ -317,7 +317,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words);
 
 int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
-  static const bool graphs_on = !(getenv("KBP_GRAPHS") && atoi(getenv("KBP_GRAPHS")) == 0);
+  static const bool graphs_on = kbp::graphs_enabled();
   static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
   int64_t n_ops = 0;
   if (!graphs_on || c->profile || sync_every || n_words < 256 || !program_is_sync_free(w, n_words, &n_ops) || n_ops < 32)

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <unordered_map>
 
@@ -48,6 +49,18 @@ inline cudaError_t stream_wait(const Arena& a) {
   cudaError_t e = cudaEventRecord(a.block_event, a.stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(a.block_event);
+}
+
+// CUDA graphs (whole sync-free programs in kbp_run, the first round of each subspace-iteration SVD): on by default,
+// KBP_GRAPHS=0/1 decides explicitly.  Under Nsight Compute they are off unless asked for: on this toolchain the tool aborts
+// on stream capture from several threads with cluster launches, and a kernel-by-kernel profile wants plain launches anyway.
+inline bool graphs_enabled() {
+  static const bool on = [] {
+    if (const char* e = getenv("KBP_GRAPHS")) return atoi(e) != 0;
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) return false;
+    return true;
+  }();
+  return on;
 }
 
 enum GemmOp { OP_N = 0, OP_T = 1, OP_C = 2, OP_J = 3 };   // as-is, transpose, conj-transpose, conj

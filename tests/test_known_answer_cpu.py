@@ -1,0 +1,40 @@
+"""End-to-end known answer: the reference's own best D=2 unit cell of the Kagome Heisenberg AFM
+(data/unit_cells/best) re-measured by the reference (tests/golden/best_D2.npz, tools/make_golden_best.py).  The oracle
+pipeline -- BP from uniform messages, ToCore chains, core -> mode -> edge, two-site RDMs -- must reproduce the reference's
+edge energies to 1e-8 and land on the published variational energy of the file name to the 3e-4 config dependence."""
+import numpy as np
+import pytest
+
+from helpers import golden
+
+
+def oracle_edge_energies(g, N):
+    from kagomeperiodicbp_b200 import edge_env
+    from oracle import bp_np, ite_np
+    from oracle.bubblecon_np import bubblecon as obub
+    chi_bp, chi, iters, term, damping = g[f"N{N}_cfg"].tolist()
+    cell = (g["A"], g["B"], g["C"])
+    cfg = bp_np.BPConfigNP(trunc_dim=int(chi_bp), msg_diff_terminate=term, damping=None if damping < 0 else damping)
+    msgs, st = bp_np.belief_propagation(N, cell, bp_np.uniform_messages(N, 2), cfg)
+    bu = bp_np.outgoing_message(N, cell, msgs, "U", int(chi), depth="ToCore")
+    td = bp_np.outgoing_message(N, cell, msgs, "D", int(chi), depth="ToCore")
+    env12 = edge_env.core_env_tensors(ite_np.NP, N, bu.A, td.A)
+    fn = lambda T, E, A, ang, order, c, kets: obub(T, E, A, ang, order, D_trunc=c, ket_tensors=kets).A
+    out = {}
+    for e in g[f"N{N}_edges"].tolist():
+        ti, tj, env, info = edge_env.edge_environment(ite_np.NP, N, cell, env12, "A", e, int(chi), fn)
+        rho = ite_np.rho_ij(ti, tj, env)
+        out[e] = float(np.real(np.dot(rho.flatten(), g["h"].flatten())))
+    return out, st
+
+
+@pytest.mark.parametrize("N", [2, 3])
+def test_best_unit_cell_energy(N):
+    g = golden("best_D2.npz")
+    energies, st = oracle_edge_energies(g, N)
+    ref = dict(zip(g[f"N{N}_edges"].tolist(), g[f"N{N}_edge_energies"].tolist()))
+    assert st["iterations"] == int(g[f"N{N}_cfg"][2])
+    for e, v in ref.items():
+        assert abs(energies[e] - v) < 1e-8, (e, energies[e], v)
+    per_site = sum(energies.values()) / 3
+    assert abs(per_site - float(g["file_energy"][0])) < 3e-4

@@ -129,13 +129,22 @@ def swallow_ket_T(mp: MPS, ket_T, i0, i1, in_legs, out_legs) -> MPS:
 
 
 def bubblecon(T_list, edges_list, angles_list, bubble_angle, swallow_order, D_trunc=None,
-              eps=None, break_points=(), ket_tensors=None, separate_exp=False):
+              eps=None, break_points=(), ket_tensors=None, separate_exp=False, compression=None):
     """main loop (src/libs/bubblecon.py:2465-3107): root tensor -> MPS, then for each vertex in
     ``swallow_order`` find the contiguous MPS legs that point at it, swallow it, and truncate the
     whole boundary MPS with ``reduceD(D_trunc, eps, nr_bulk=True)``."""
     n = len(T_list)
     if ket_tensors is None:
         ket_tensors = [False] * n
+    # compression = {'type': 'SVD'} | {'type': 'iter', 'max-iter': ..., 'err': ...}      (:2612-2624, 2793-2798, 3035-3038)
+    comp_type = "SVD" if compression is None else compression.get("type", "SVD")
+
+    def compress(m):
+        if comp_type == "SVD":
+            m.reduceD(D_trunc, eps, nr_bulk=True)
+        else:
+            from .reduce_iter_np import reduceDiter
+            reduceDiter(m, D_trunc, nr_bulk=True, max_iter=compression["max-iter"], err=compression["err"])
     # edge -> (i, j) vertex pair; open edges map to (i, i)          (:2654-2664)
     vertices = {}
     for i in range(n):
@@ -152,7 +161,7 @@ def bubblecon(T_list, edges_list, angles_list, bubble_angle, swallow_order, D_tr
     T_root = fuse_tensor(T_list[root]) if ket_tensors[root] else T_list[root]
     mp = tensor_to_MPS_ID(T_root.transpose(perm))
     if D_trunc is not None:
-        mp.reduceD(D_trunc, eps, nr_bulk=True)
+        compress(mp)
 
     snapshots = []
     for l in range(1, len(swallow_order)):
@@ -180,7 +189,7 @@ def bubblecon(T_list, edges_list, angles_list, bubble_angle, swallow_order, D_tr
         else:
             mp = swallow_T(mp, T_list[v], i0, i1, in_legs, out_legs)
         if D_trunc is not None:
-            mp.reduceD(D_trunc, eps, nr_bulk=True)
+            compress(mp)
         mp_edges = mp_edges[:i0] + [v_edges[i] for i in out_legs] + mp_edges[i1 + 1:]
 
     if not mp_edges and not snapshots:                                          # (:3077-3088)

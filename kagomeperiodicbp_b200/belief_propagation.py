@@ -73,6 +73,20 @@ class KagomeTNRepeatedUnitCell:
         return self.lattice.message_indices(side)
 
 
+class KagomeTNArbitrary(KagomeTNRepeatedUnitCell):
+    """the block with an independent tensor on every lattice site (src/tensor_networks/tensor_network.py:400-431): same BP and
+    measurement entry points, `unit_cell` is a `LatticeTensors`.  The lattice size follows from the number of tensors."""
+
+    def __init__(self, tensors):
+        from .containers import LatticeTensors
+        n = len(tensors)
+        N = next((k for k in range(2, 64) if len(get_block(k).sites) == n), None)
+        if N is None:
+            raise ValueError(f"{n} tensors do not fill a Kagome block")
+        lt = tensors if isinstance(tensors, LatticeTensors) else LatticeTensors(tensors)
+        super().__init__(lt, N)
+
+
 def kagome_tn_from_unit_cell(unit_cell: UnitCell, dims) -> KagomeTNRepeatedUnitCell:
     """(src/tensor_networks/construction.py:45-52)"""
     return KagomeTNRepeatedUnitCell(unit_cell, dims.big_lattice_size, dims.physical_dim, dims.virtual_dim)
@@ -148,8 +162,9 @@ def _node_tensor(k: int, L: int, t):
 
 
 def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes, damping, depth="ToMessage",
-                         epilogue=True) -> Compiled:
-    key = ("side", N, d, D, side, chi, msg_shapes, damping, depth, epilogue)
+                         epilogue=True, arbitrary=False) -> Compiled:
+    """`arbitrary`: one input tensor per lattice site ("site{i}", the non-repeated block) instead of the unit cell's three."""
+    key = ("side", N, d, D, side, chi, msg_shapes, damping, depth, epilogue, arbitrary)
     if key in _cache:
         return _cache[key]
     blk = get_block(N)
@@ -157,9 +172,9 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
     p = Program(N_SLOTS)
     ins = []
     cell_dt = []
-    for nm in "ABC":
-        t = p.input(f"cell{nm}", (d, D, D, D, D))
-        ins.append((f"cell{nm}", t))
+    for nm in ([f"site{s_.index}" for s_ in blk.sites] if arbitrary else ["cellA", "cellB", "cellC"]):
+        t = p.input(nm, (d, D, D, D, D))
+        ins.append((nm, t))
         cell_dt.append(t)
     used = [s for s in BLOCK_SIDES_CCW if s != side] if depth == "ToMessage" else list(BLOCK_SIDES_CCW)
     msg_dt = {}
@@ -178,7 +193,7 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
     T, E, A = block_tn.connect_corner(N, T, E, A, P, side)
     TL = [None] * len(T)
     for s_ in blk.sites:
-        TL[s_.index] = cell_dt[s_.index % 3]
+        TL[s_.index] = cell_dt[s_.index] if arbitrary else cell_dt[s_.index % 3]
     for s in BLOCK_SIDES_CCW:
         for k, idx in enumerate(blk.message_indices(s)):
             if s in msg_dt:
@@ -214,8 +229,15 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
     return comp
 
 
-def _side_inputs(cell: UnitCell, messages: dict, comp: Compiled) -> dict:
-    d = {"cellA": cell.A, "cellB": cell.B, "cellC": cell.C}
+def _is_arbitrary(cell) -> bool:
+    return hasattr(cell, "site_tensors")
+
+
+def _side_inputs(cell, messages: dict, comp: Compiled) -> dict:
+    if _is_arbitrary(cell):
+        d = {f"site{i}": t for i, t in enumerate(cell.site_tensors)}
+    else:
+        d = {"cellA": cell.A, "cellB": cell.B, "cellC": cell.C}
     names = {n for n, _, _ in comp.in_layout}
     for s in BLOCK_SIDES_CCW:
         for k, a in enumerate(messages[s].mps.A):
@@ -241,7 +263,7 @@ def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device
     damping = config.damping if config.damping else None
     futs = []
     for side in (BLOCK_SIDES_CCW if sides is None else sides):
-        comp = compile_side_program(N, d, D, side, config.trunc_dim, shapes, damping)
+        comp = compile_side_program(N, d, D, side, config.trunc_dim, shapes, damping, arbitrary=_is_arbitrary(cells[0]))
         batch = [_side_inputs(c, m, comp) for c, m in zip(cells, messages_list)]
         futs.append(_pool.submit(_run_side, side, comp, batch, device))
     res = {}

@@ -37,12 +37,13 @@ def message_node_positions(blk: KagomeBlock, side: str):
 
 
 def assemble(N: int, cell, messages: dict | None):
-    """``cell`` = (A, B, C) arrays [d, D, D, D, D]; ``messages`` = {side: [site arrays [DL, D^2, DR]]}.
-    Returns lists indexed by node: tensors, edges, angles, kets, positions."""
+    """``cell`` = (A, B, C) arrays [d, D, D, D, D] (repeated unit cell) or one tensor per lattice site in block-index order (the
+    non-repeated block, KagomeTNArbitrary: src/tensor_networks/tensor_network.py:400-431); ``messages`` = {side: [site arrays
+    [DL, D^2, DR]]}.  Returns lists indexed by node: tensors, edges, angles, kets, positions."""
     blk = get_block(N)
     tensors, edges, angles, kets, pos = [], [], [], [], []
     for s in blk.sites:
-        tensors.append(cell[s.index % 3])
+        tensors.append(cell[s.index % 3] if len(cell) == 3 else cell[s.index])
         edges.append(list(s.edges))
         angles.append(list(s.angles))
         kets.append(True)

@@ -127,6 +127,24 @@ class Config:
         self.bp.trunc_dim = int(v)
 
 
+class LatticeTensors:
+    """one independent site tensor [d, D, D, D, D] per lattice site of the block, in block-index order (what the reference's
+    KagomeTNArbitrary holds, src/tensor_networks/tensor_network.py:400-431); leg orders by site kind as in UnitCell."""
+
+    def __init__(self, site_tensors):
+        self.site_tensors = [np.asarray(t) for t in site_tensors]
+
+    @property
+    def A(self):                      # shape queries (d, D) of the callers
+        return self.site_tensors[0]
+
+    def tensors(self):
+        return tuple(self.site_tensors)
+
+    def copy(self) -> "LatticeTensors":
+        return LatticeTensors([t.copy() for t in self.site_tensors])
+
+
 @dataclass
 class UnitCell:
     """three site tensors [d, D, D, D, D] of one upper triangle; leg orders

@@ -125,8 +125,11 @@ def core_network(B, N: int, cell, env12):
     tb = tables()["core"]
     flavor = {"A": 0, "B": 1, "C": 2}
     kets = {}
+    core_idx = core_site_indices(N)
     for k in range(9):
-        kets[k] = (np.asarray(cell[flavor[tb[k]["name"]]]), list(tb[k]["edges"]))
+        # repeated unit cell: by flavor; non-repeated block (one tensor per lattice site): the core site's own tensor
+        t = cell[flavor[tb[k]["name"]]] if len(cell) == 3 else cell[core_idx[k]]
+        kets[k] = (np.asarray(t), list(tb[k]["edges"]))
     envs = {}
     for i in range(12):
         envs[i] = Node(env12[i], list(tb[9 + i]["edges"]))

@@ -49,7 +49,7 @@ def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device
     shapes = bp._msg_shapes(messages)
     futs = []
     for side in (bu_side, td_side):
-        comp = bp.compile_side_program(N, d, D, side, chi, shapes, None, depth="ToCore", epilogue=False)
+        comp = bp.compile_side_program(N, d, D, side, chi, shapes, None, depth="ToCore", epilogue=False, arbitrary=bp._is_arbitrary(unit_cell))
         batch = [bp._side_inputs(unit_cell, messages, comp)]
         futs.append(bp._pool.submit(bp._run_side, side, comp, batch, device))
     res = {}

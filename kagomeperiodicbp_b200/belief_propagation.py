@@ -86,6 +86,21 @@ class KagomeTNArbitrary(KagomeTNRepeatedUnitCell):
         lt = tensors if isinstance(tensors, LatticeTensors) else LatticeTensors(tensors)
         super().__init__(lt, N)
 
+    @property
+    def tensors(self):
+        return list(self.unit_cell.site_tensors)
+
+    def shift_periodically_in_direction(self, direction: str) -> "KagomeTNArbitrary":
+        """(src/tensor_networks/tensor_network.py:491-496)"""
+        from . import shifting
+        return KagomeTNArbitrary(shifting.shift_tensors(self.tensors, shifting.shift_permutation(self.N, direction)))
+
+    def all_lattice_shifting_options(self):
+        """every periodic translation of the block, the identity first (src/tensor_networks/tensor_network.py:484-489)"""
+        from . import shifting
+        for perm in shifting.all_shift_permutations(self.N):
+            yield KagomeTNArbitrary(shifting.shift_tensors(self.tensors, perm))
+
 
 def kagome_tn_from_unit_cell(unit_cell: UnitCell, dims) -> KagomeTNRepeatedUnitCell:
     """(src/tensor_networks/construction.py:45-52)"""

@@ -47,3 +47,14 @@ def test_arbitrary_block_on_device():
     m = ite_flow.measure_energies(tn.unit_cell, msgs, 2, chi, g["h"], mode="A")
     for e, v in ref.items():
         assert abs(m.energies[f"({e[0]}, {e[1]})"] - v) < 1e-8, (e, m.energies)
+
+
+def test_shift_averaged_measurement_on_device():
+    from kagomeperiodicbp_b200 import shifting
+    from kagomeperiodicbp_b200.containers import BPConfig
+    g = golden("shifting.npz")
+    sites = [g[f"site{i}"] for i in range(21)]
+    chi_bp, chi, term, damping = g["cfg"].tolist()
+    cfg = BPConfig(trunc_dim=int(chi_bp), msg_diff_terminate=term, damping=damping, init_msg="UQ")
+    e = shifting.calc_measurement_non_unit_cell_kagome_tn(sites, cfg, int(chi))
+    assert abs(e - float(g["measurement"][0])) < 1e-8

@@ -58,3 +58,22 @@ def test_shift_averaged_measurement_on_device():
     cfg = BPConfig(trunc_dim=int(chi_bp), msg_diff_terminate=term, damping=damping, init_msg="UQ")
     e = shifting.calc_measurement_non_unit_cell_kagome_tn(sites, cfg, int(chi))
     assert abs(e - float(g["measurement"][0])) < 1e-8
+
+
+def test_bp_step_is_bitwise_reproducible():
+    """run-to-run determinism on one GPU (SURVEY 8b conventions): no atomics on data, split-K partials and the cluster kernels'
+    partial sums are added in a fixed order, so two executions of the same step agree bit for bit."""
+    from kagomeperiodicbp_b200 import belief_propagation as bp
+    from kagomeperiodicbp_b200.containers import BPConfig, UnitCell
+    from helpers import SIDES
+    D, N = 4, 2
+    cell = UnitCell.random(2, D, seed=9)
+    tn = bp.KagomeTNRepeatedUnitCell(cell, N)
+    tn.connect_uniform_messages()
+    cfg = BPConfig(trunc_dim=2 * D * D, msg_diff_terminate=1e-6, damping=0.1, init_msg="UQ")
+    runs = [bp.bp_step_batch(N, [cell], [tn.messages], cfg)[0] for _ in range(3)]
+    for r in runs[1:]:
+        assert r[2] == runs[0][2]
+        for s in SIDES:
+            for a, b in zip(r[0][s].mps.A, runs[0][0][s].mps.A):
+                assert np.array_equal(a, b)

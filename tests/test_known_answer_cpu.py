@@ -8,14 +8,14 @@ import pytest
 from helpers import golden
 
 
-def oracle_edge_energies(g, N):
+def oracle_edge_energies(g, N, D=2):
     from kagomeperiodicbp_b200 import edge_env
     from oracle import bp_np, ite_np
     from oracle.bubblecon_np import bubblecon as obub
     chi_bp, chi, iters, term, damping = g[f"N{N}_cfg"].tolist()
     cell = (g["A"], g["B"], g["C"])
     cfg = bp_np.BPConfigNP(trunc_dim=int(chi_bp), msg_diff_terminate=term, damping=None if damping < 0 else damping)
-    msgs, st = bp_np.belief_propagation(N, cell, bp_np.uniform_messages(N, 2), cfg)
+    msgs, st = bp_np.belief_propagation(N, cell, bp_np.uniform_messages(N, D), cfg)
     bu = bp_np.outgoing_message(N, cell, msgs, "U", int(chi), depth="ToCore")
     td = bp_np.outgoing_message(N, cell, msgs, "D", int(chi), depth="ToCore")
     env12 = edge_env.core_env_tensors(ite_np.NP, N, bu.A, td.A)
@@ -28,13 +28,13 @@ def oracle_edge_energies(g, N):
     return out, st
 
 
-@pytest.mark.parametrize("N", [2, 3])
-def test_best_unit_cell_energy(N):
-    g = golden("best_D2.npz")
-    energies, st = oracle_edge_energies(g, N)
+@pytest.mark.parametrize("D,N,band", [(2, 2, 3e-4), (2, 3, 3e-4), (3, 2, 3e-3)])
+def test_best_unit_cell_energy(D, N, band):
+    g = golden(f"best_D{D}.npz")
+    energies, st = oracle_edge_energies(g, N, D)
     ref = dict(zip(g[f"N{N}_edges"].tolist(), g[f"N{N}_edge_energies"].tolist()))
     assert st["iterations"] == int(g[f"N{N}_cfg"][2])
     for e, v in ref.items():
         assert abs(energies[e] - v) < 1e-8, (e, energies[e], v)
     per_site = sum(energies.values()) / 3
-    assert abs(per_site - float(g["file_energy"][0])) < 3e-4
+    assert abs(per_site - float(g["file_energy"][0])) < band          # config dependence of the published value (N, chi)

@@ -77,3 +77,23 @@ def test_bp_step_is_bitwise_reproducible():
         for s in SIDES:
             for a, b in zip(r[0][s].mps.A, runs[0][0][s].mps.A):
                 assert np.array_equal(a, b)
+
+
+def test_best_D3_unit_cell_energy_on_device():
+    """the D=3 case of tests/test_known_answer_gpu.py (the D=2 cases there were run on the B200; this fixture came later)"""
+    from kagomeperiodicbp_b200 import belief_propagation as bp
+    from kagomeperiodicbp_b200 import ite_flow
+    from kagomeperiodicbp_b200.containers import BPConfig, UnitCell
+    g = golden("best_D3.npz")
+    N = 2
+    chi_bp, chi, iters, term, damping = g[f"N{N}_cfg"].tolist()
+    cell = UnitCell(g["A"], g["B"], g["C"])
+    cfg = BPConfig(trunc_dim=int(chi_bp), msg_diff_terminate=term, damping=None if damping < 0 else damping, init_msg="UQ")
+    tn = bp.KagomeTNRepeatedUnitCell(cell, N)
+    tn.connect_uniform_messages()
+    msgs, stats = bp.belief_propagation(tn, tn.messages, cfg)
+    assert stats.iterations == int(iters)
+    m = ite_flow.measure_energies(cell, msgs, N, int(chi), g["h"], mode="A")
+    ref = dict(zip(g[f"N{N}_edges"].tolist(), g[f"N{N}_edge_energies"].tolist()))
+    for e, v in ref.items():
+        assert abs(m.energies[f"({e[0]}, {e[1]})"] - v) < 1e-8, (e, m.energies, v)

@@ -46,8 +46,7 @@ enum {
   KBP_OP_PERMUTE = 1,        /* dst, src, conj, ndim, dims_src[ndim], perm[ndim] */
   KBP_OP_GEMM = 2,           /* C, A, B, m, n, k, opA, opB      op: 0 N, 1 T, 2 C (conj-transpose), 3 J (conj) */
   KBP_OP_QR = 3,             /* A, Q, R, work, m, n */
-  KBP_OP_SVD = 4,            /* A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, warm (offset of a persistent
-                                kbp_svd_warm_elems buffer or -1) */
+  KBP_OP_SVD = 4,            /* A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, reserved (-1) */
   KBP_OP_NORMALIZE = 5,      /* buf, n, slot_lognorm */
   KBP_OP_EMBED = 6,          /* dst, src, alpha_re(bits), alpha_im(bits), d0, d1, d2, s0, s1, s2, sign_slot */
   KBP_OP_ZERO = 7,           /* dst, n */
@@ -74,22 +73,33 @@ int kbp_broadcast(kbp_ctx* ctx, int64_t offset, const void* host, int64_t n_elem
 int kbp_slots_read(kbp_ctx* ctx, double* host);      /* nb * n_slots doubles */
 int kbp_slots_zero(kbp_ctx* ctx);
 
-/* run a tensor program on all chains (asynchronous except for one flag read per Jacobi sweep) */
+/* run a tensor program on all chains.  From its second run on a program executes as ONE CUDA graph launch: the call is
+ * asynchronous and no decision is taken on the host (the data-dependent loops of the truncated SVDs are conditional graph
+ * nodes driven by device-side decision kernels).  The first run of a program, and every run when graphs are disabled
+ * (KBP_GRAPHS=0, under Nsight Compute, with per-op profiling on), is host-driven: plain launches, one small read-back per
+ * SVD decision.  kbp_graph_ready tells which of the two the next kbp_run of this program will be (1 = graph launch). */
 int kbp_run(kbp_ctx* ctx, const int64_t* words, int64_t n_words);
+int kbp_graph_ready(kbp_ctx* ctx, const int64_t* words, int64_t n_words);
+/* programs shorter than min_words are never captured (default 256); capture_first != 0: capture at first sight (default: second) */
+int kbp_graph_policy(kbp_ctx* ctx, int64_t min_words, int capture_first);
 int kbp_sync(kbp_ctx* ctx);
 
 /* workspace sizes (complex128 elements) needed by KBP_OP_SVD / KBP_OP_QR */
 int64_t kbp_svd_work_elems(int64_t m, int64_t n);
 int64_t kbp_qr_work_elems(int64_t m, int64_t n);
-/* persistent buffer in which KBP_OP_SVD keeps its Ritz basis between runs of the same program (0: op never uses one) */
+/* reserved (size of a persistent per-op buffer; always 0: KBP_OP_SVD keeps no state between runs) */
 int64_t kbp_svd_warm_elems(int64_t m, int64_t n, int64_t keep);
 
 /* instrumentation: kernels launched so far; device timing of a region on the context's stream */
 int64_t kbp_launch_count(const kbp_ctx* ctx);
-int64_t kbp_svd_sweeps(const kbp_ctx* ctx);           /* total Jacobi sweeps / subspace iterations so far */
-/* out8[1] truncations done by the in-shared-memory Jacobi kernel, [2] by subspace iteration, [3] subspace iterations that
- * fell back to the exact path, [4] by the block-Jacobi kernel, [5] subspace iterations in total */
-int kbp_svd_counters(const kbp_ctx* ctx, int64_t* out8);
+int64_t kbp_svd_sweeps(kbp_ctx* ctx);                 /* total block-Jacobi sweeps + subspace iterations so far (synchronises) */
+/* how the truncations were executed so far (synchronises; [2..7] are counted on the device by the decision kernels):
+ * out8[0] Householder reduction + in-shared-memory Jacobi, [1] in-shared-memory Jacobi, [2] accepted from subspace iteration,
+ * [3] handed by the subspace iteration to the exact path, [4] exact (block-Jacobi) runs, [5] subspace iterations in total,
+ * [6] block-Jacobi sweeps, [7] truncations that did not converge */
+int kbp_svd_counters(kbp_ctx* ctx, int64_t* out8);
+/* out4[0] graph launches so far, [1] programs captured, [2] graphs alive, [3] programs whose capture failed */
+int kbp_graph_counters(const kbp_ctx* ctx, int64_t* out4);
 int kbp_timer_start(kbp_ctx* ctx);
 int kbp_timer_stop_ms(kbp_ctx* ctx, double* ms);       /* synchronises */
 /* per-opcode device time: when enabled, kbp_run brackets every op with CUDA events on the context's stream;

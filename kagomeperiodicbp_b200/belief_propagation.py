@@ -24,7 +24,7 @@ from . import block_tn, contraction_order
 from .containers import BPConfig, BPStats, Message, MPSOrientation, UnitCell
 from .dev_bubblecon import trace_bubblecon
 from .dev_mps import SLOT_LOGNORM, SLOT_NONFINITE, SLOT_TRUNC, DevMPS, add_two_mps, inner_product
-from .engine import E_SVD_NOCONV, BubbleConError
+from .engine import E_SVD_NOCONV, BubbleConError, raise_if_not_converged
 from .lattice import BLOCK_SIDES_CCW, SIDE_ANGLE, SIDE_OPPOSITE, get_block
 from .mps import MPS
 from .program import Program
@@ -276,12 +276,24 @@ def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device
     for m in messages_list[1:]:
         assert _msg_shapes(m) == shapes, "batched cells must share message shapes"
     damping = config.damping if config.damping else None
-    futs = []
+    if config.fix_msg_each_step is False:
+        raise NotImplementedError("BPConfig.fix_msg_each_step=False: the side programs always normalise the new message "
+                                  "(the reference's default, src/algo/belief_propagation.py:158-159)")
+    todo = []
     for side in (BLOCK_SIDES_CCW if sides is None else sides):
         comp = compile_side_program(N, d, D, side, config.trunc_dim, shapes, damping, arbitrary=_is_arbitrary(cells[0]))
         batch = [_side_inputs(c, m, comp) for c, m in zip(cells, messages_list)]
-        futs.append(_pool.submit(_run_side, side, comp, batch, device))
+        todo.append((side, comp, batch, get_engine(("side", side), device)))
     res = {}
+    if all(eng.graph_ready(comp.words) for _, comp, _, eng in todo):
+        # steady state: every side program is one CUDA-graph launch on its own stream -- queue all of them from this thread,
+        # then collect; the host takes no part in the iteration and no launch thread spins on a stream
+        rcs = [comp.launch(eng, batch, soft_errors=(E_SVD_NOCONV,)) for _, comp, batch, eng in todo]
+        for (side, comp, batch, eng), rc in zip(todo, rcs):
+            res[side] = comp.collect(eng, len(batch), rc)
+        return res
+    # first sight of a program (or graphs disabled / a profiler attached): host-driven loops, one launch thread per side
+    futs = [_pool.submit(_run_side, side, comp, batch, device) for side, comp, batch, _ in todo]
     for f in futs:
         side, outs, slots, rc = f.result()
         res[side] = (outs, slots, rc)
@@ -297,6 +309,8 @@ def assemble_step(res: dict, n_cells: int, config: BPConfig):
         out_msgs, next_msgs, dists, trunc = {}, {}, [], 0.0
         for side in BLOCK_SIDES_CCW:
             outs, slots, rc = res[side]
+            if slots[ci, -1] > 0:                                  # engine status slot: a truncation of this chain did not converge
+                raise_if_not_converged(E_SVD_NOCONV, f"block message towards {side}")
             if slots[ci, SLOT_NONFINITE] > 0:
                 raise BubbleConError(f"non-finite values in the outgoing message towards {side}")
             opp = SIDE_OPPOSITE[side]
@@ -362,8 +376,9 @@ def _hermitize_messages(messages: dict) -> dict:
     def one(side):
         m = messages[side]
         comp = _hermitize_program([a.shape for a in m.mps.A])
-        outs, _, _ = comp.run(get_engine(("side", side)), [{f"s{k}": a for k, a in enumerate(m.mps.A)}],
-                              soft_errors=(E_SVD_NOCONV,))
+        outs, _, rc = comp.run(get_engine(("side", side)), [{f"s{k}": a for k, a in enumerate(m.mps.A)}],
+                               soft_errors=(E_SVD_NOCONV,))
+        raise_if_not_converged(rc, f"hermitisation of the message of side {side}")
         o = outs[0]
         return side, Message(MPS.from_sites([o[f"o{k}"] for k in range(m.mps.N)]), m.orientation)
     return dict(_pool.map(one, list(messages.keys())))

@@ -24,7 +24,7 @@ import numpy as np
 
 from .dev_bubblecon import fuse_tensor, swallow_ket_T, swallow_T, tensor_to_mps_id, trace_bubblecon
 from .dev_mps import SLOT_LOGNORM, SLOT_NONFINITE, SLOT_TRUNC, DevMPS
-from .engine import E_SVD_NOCONV, BubbleConError
+from .engine import E_SVD_NOCONV, BubbleConError, raise_if_not_converged
 from .mps import MPS
 from .program import Program
 from .runtime import Compiled, get_engine
@@ -215,6 +215,7 @@ def bubblecon(T_list, edges_list, angles_list, bubble_angle, swallow_order, D_tr
     if slots[0, SLOT_NONFINITE] > 0:
         raise BubbleConError("bubblecon: the boundary MPS contains nan/inf values")      # reference bmpslib.py:711-717
     last_stats.update(trunc_error=float(slots[0, SLOT_TRUNC]), svd_noconv=(rc == E_SVD_NOCONV), flops=comp.flops)
+    raise_if_not_converged(rc, "bubblecon")
     n_out = comp.meta["n_out"]
     mp = MPS.from_sites([outs[0][f"o{k}"] for k in range(n_out)], ln_scale=float(slots[0, SLOT_LOGNORM]))
     if not comp.meta["edges"]:

@@ -31,6 +31,8 @@ struct GemmArgs {
   double2* scratch;               // [nb][scratch_stride]
   long long scratch_stride;
   int* counters;                  // [nb][GEMM_MAX_TILES], zero between launches
+  const int* mask;                // per-chain predicate (kbp_ops.cuh: Arena::mask)
+  int mask_want;
 };
 
 constexpr int GEMM_MAX_TILES = 4096;
@@ -57,6 +59,7 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
   cplx* Bs = As + STAGES * TA;                                   // [STAGES][TB]
 
   const int chain = blockIdx.z / g.ksplit, split = blockIdx.z - chain * g.ksplit;
+  if (g.mask && g.mask[chain] != g.mask_want) return;
   cplx* Cb = base + (long long)chain * chain_stride + g.C + (long long)split * g.m * g.n;
   const cplx* Ab = base + (long long)chain * chain_stride + g.A;
   const cplx* Bb = base + (long long)chain * chain_stride + g.B;
@@ -224,11 +227,6 @@ static void launch_gemm(const Arena& a, GemmArgs g) {
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
   constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
   const unsigned tn = (unsigned)((g.n + BN - 1) / BN), tm = (unsigned)((g.m + BM - 1) / BM);
   g.rows_on_x = tm > tn;
   dim3 grid(g.rows_on_x ? tm : tn, g.rows_on_x ? tn : tm, (unsigned)(a.nb * g.ksplit));
@@ -238,7 +236,7 @@ static void launch_gemm(const Arena& a, GemmArgs g) {
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
   if (m == 0 || n == 0) return;
-  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev};
+  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev, a.mask, a.mask_want};
   if (ksplit == 0) {
     // automatic: a small product is bound by how many warps (16x8 accumulator tiles) it offers to the 592 sub-partitions;
     // split k (fused, deterministic reduction) until there are enough, keeping >= 4 slabs per split
@@ -264,6 +262,20 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
   else if (ctas64 >= 96) launch_gemm<64, 64, 3, 8>(a, g);
   else if (ctas32 >= 96) launch_gemm<32, 32, 4, 8>(a, g);
   else launch_gemm<16, 16, 4, 2>(a, g);
+}
+
+template <int BM, int BN, int STAGES, int NWARPS>
+static void gemm_attr() {
+  constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
+  constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
+  constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
+  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+void init_gemm_attributes() {
+  gemm_attr<16, 16, 4, 2>();
+  gemm_attr<32, 32, 4, 8>();
+  gemm_attr<64, 64, 3, 8>();
 }
 
 void gemm(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB) {

@@ -269,11 +269,6 @@ bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int6
   int C = 1;
   while (C <= 8 && ((m + C - 1) / C > QRC_MLOC_MAX || qrc_smem((int)m, (int)n, C) > QRC_SMEM_MAX)) C <<= 1;
   if (C > 8) return false;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QRC_SMEM_MAX);
-    attr_set = true;
-  }
   QrcArgs g;
   g.A = A; g.Q = Q; g.R = R; g.m = (int)m; g.n = (int)n;
   cudaLaunchConfig_t cfg = {};
@@ -295,5 +290,7 @@ bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int6
   ++*a.launches;
   return true;
 }
+
+void init_qr_attributes() { cudaFuncSetAttribute(qr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QRC_SMEM_MAX); }
 
 }  // namespace kbp

@@ -60,13 +60,9 @@ bool svd_small_fits(int64_t m, int64_t n);
 void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
                int slot_lognorm, int slot_trunc);
 int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                          int nr_bulk, int slot_lognorm, int slot_trunc, int b, int64_t warm);
+                          int nr_bulk, int slot_lognorm, int slot_trunc, int b);
 void phase_fix(const Arena& a, int64_t Vh, int64_t US, int64_t m, int64_t n, int64_t keep, int us_too);
 
-int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep) {
-  if (svd_small_fits(m, n) || tsvd_block(m, n, keep) == 0) return 0;
-  return n * 112;
-}
 
 int64_t svd_work_elems(int64_t m, int64_t n) {
   SvdGeom g = svd_geom(m, n);
@@ -75,7 +71,9 @@ int64_t svd_work_elems(int64_t m, int64_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void svd_init_kernel(cplx* __restrict__ base, long long chain_stride, long long A_, long long Z_, SvdGeom g) {
+__global__ void svd_init_kernel(cplx* __restrict__ base, long long chain_stride, long long A_, long long Z_, SvdGeom g,
+                                const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
   cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* A = cb + A_;
   cplx* Z = cb + Z_;
@@ -128,7 +126,8 @@ __device__ __forceinline__ unsigned long long dbl_bits_nonneg(double x) { return
 
 __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base, long long chain_stride, long long Z_, SvdGeom g,
                                                         int round, double tol, const double* __restrict__ off_prev,
-                                                        double* __restrict__ off_cur, const double* __restrict__ fro2, int inner_max) {
+                                                        double* __restrict__ off_cur, const double* __restrict__ fro2, int inner_lo,
+                                                        const SvdCtl* __restrict__ ctl) {
   // shared: staged operand planes (phase 1) reused as W^H planes (phase 3); G and W for the eigensolve
   extern __shared__ __align__(16) unsigned char svd_smem[];
   cplx (*Gs)[PR + 1] = reinterpret_cast<cplx (*)[PR + 1]>(svd_smem);
@@ -140,7 +139,8 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
   __shared__ int perm[PR];
 
   const int chain = blockIdx.y;
-  if (off_prev[chain] < tol) return;            // this chain converged in the previous sweep
+  if (off_prev[chain] < tol) return;            // this chain converged in the previous sweep (or takes no part)
+  const int inner_max = ctl->sweeps < 24 ? inner_lo : 15;
   // rows whose norm is below 1e-17 ||A||_F are rounding residue of exactly dependent rows: treated as zero
   const double floor2 = 1e-34 * fro2[chain];
   cplx* Z = base + (long long)chain * chain_stride + Z_;
@@ -348,7 +348,9 @@ __global__ void __launch_bounds__(256) svd_round_kernel(cplx* __restrict__ base,
 // one CTA per chain: row norms -> singular values, rank sort, write U_k S_k and V_k^H, update slots
 __global__ void __launch_bounds__(1024) svd_extract_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
                                                            int n_slots, long long Z_, long long US_, long long Vh_, SvdGeom g,
-                                                           int keep, int nr_bulk, int slot_lognorm, int slot_trunc) {
+                                                           int keep, int nr_bulk, int slot_lognorm, int slot_trunc, const int* __restrict__ mask,
+                                                           int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   extern __shared__ double dyn[];
   double* s2 = dyn;                                   // p_pad
   int* idx = reinterpret_cast<int*>(dyn + g.p_pad);   // keep
@@ -429,14 +431,147 @@ __global__ void fill_kernel(double* p, int n, double v) {
   if (i < n) p[i] = v;
 }
 
-static int svd_truncate_jacobi(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                               int nr_bulk, int slot_lognorm, int slot_trunc);
+// ------------------------------------------------------------------------------------------------
+// Sweep control on the device (one thread each).  begin: which chains take part (off_prev = huge), zero the sweep counter.
+// end of a sweep: this sweep's measure becomes the next one's "previous"; another sweep iff some chain is above tolerance and
+// the budget is not spent; a chain that runs out of budget is reported in the engine's status slot (include/kbp.h).
+__global__ void svd_exact_begin_kernel(SvdCtl* __restrict__ ctl, const int* __restrict__ mask, int mask_want, double* __restrict__ off_prev, int nb,
+                                       cudaGraphConditionalHandle h_sweep, int use_handle) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int any = 0;
+  for (int c = 0; c < nb; ++c) {
+    const bool on = !mask || mask[c] == mask_want;
+    off_prev[c] = on ? 1e300 : 0.0;
+    if (on) { any = 1; ctl->counters[4] += 1; }
+  }
+  ctl->sweeps = 0;
+  ctl->any_sweep = any;
+  if (use_handle) cudaGraphSetConditional(h_sweep, any ? 1u : 0u);
+}
 
-// Dispatcher: in-smem Jacobi for small matrices, subspace iteration when only a small leading part is kept,
-// full block-Jacobi otherwise / as the exact fallback.  counters: [1] small, [2] subspace ok, [3] subspace fell back,
-// [4] block-Jacobi, [5] subspace iterations.
+__global__ void svd_exact_sweep_end_kernel(SvdCtl* __restrict__ ctl, double* __restrict__ off_prev, const double* __restrict__ off_cur, int nb,
+                                           double tol, int max_sweeps, double* __restrict__ slots, int n_slots,
+                                           cudaGraphConditionalHandle h_sweep, int use_handle) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int s = ctl->sweeps + 1;
+  int any = 0;
+  for (int c = 0; c < nb; ++c) {
+    if (!(off_prev[c] >= tol)) continue;                     // took no part in this sweep
+    double v = off_cur[c];
+    if (!(v == v)) v = 0.0;                                   // non-finite input: reported by the program's NaN guard op
+    if (v >= tol && s >= max_sweeps) {
+      slots[(long long)c * n_slots + n_slots - 1] += 1.0;
+      ctl->counters[7] += 1;
+      v = 0.0;
+    }
+    off_prev[c] = v;
+    any |= v >= tol;
+  }
+  ctl->sweeps = s;
+  ctl->counters[6] += 1;
+  ctl->any_sweep = any;
+  if (use_handle) cudaGraphSetConditional(h_sweep, any ? 1u : 0u);
+}
+
+static void svd_exact_sweep(const Arena& a, int64_t work, const SvdGeom& g, double* prev, double* cur, double* fro2, int inner_lo,
+                            cudaGraphConditionalHandle h_sweep) {
+  cudaMemsetAsync(cur, 0, sizeof(double) * a.nb, a.stream);
+  for (int r = 0; r < g.nblk - 1; ++r) {
+    svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur, fro2, inner_lo, a.ctl);
+    ++*a.launches;
+  }
+  svd_exact_sweep_end_kernel<<<1, 32, 0, a.stream>>>(a.ctl, prev, cur, a.nb, SVD_TOL, SVD_MAX_SWEEPS, a.slots, a.n_slots, h_sweep, a.capture ? 1 : 0);
+  ++*a.launches;
+}
+
+// Exact path: block one-sided Jacobi on the chains selected by a.mask (all if null).  The sweep loop is a WHILE node in
+// graph mode and a host loop over the device's control block otherwise.  Returns sweeps (host mode) or 1, < 0 on CUDA failure.
+int svd_exact(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep, int nr_bulk,
+              int slot_lognorm, int slot_trunc) {
+  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
+  static const int inner_lo = getenv("KBP_SVD_INNER") ? atoi(getenv("KBP_SVD_INNER")) : 2;
+  if (debug) fprintf(stderr, "[kbp svd %lldx%lld keep %lld] block-Jacobi path\n", (long long)m, (long long)n, (long long)keep);
+  SvdGeom g = svd_geom(m, n);
+  {
+    long long total = (long long)g.p_pad * g.ld;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    svd_init_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, A, work, g, a.mask, a.mask_want);
+    ++*a.launches;
+  }
+  // flags of the exact path live behind those of the subspace iteration (both may be in flight for different chains)
+  double* base = a.svd_off + (6 + 32 * 160) * (size_t)a.nb;
+  double* prev = base;
+  double* cur = base + a.nb;
+  double* fro2 = base + 2 * a.nb;
+  svd_fro_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, m * n, fro2);
+  ++*a.launches;
+  const cudaGraphConditionalHandle h_sweep = new_cond_handle(a);
+  svd_exact_begin_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.mask, a.mask_want, prev, a.nb, h_sweep, a.capture ? 1 : 0);
+  ++*a.launches;
+  int sweeps = 1;
+  if (a.capture) {
+    Arena body;
+    if (!begin_cond_body(a, h_sweep, true, &body)) return -1;
+    svd_exact_sweep(body, work, g, prev, cur, fro2, inner_lo, h_sweep);
+    if (!end_body(body)) return -1;
+  } else {
+    sweeps = 0;
+    while (true) {
+      svd_exact_sweep(a, work, g, prev, cur, fro2, inner_lo, h_sweep);
+      ++sweeps;
+      cudaMemcpyAsync(a.ctl_host, a.ctl, sizeof(SvdCtl), cudaMemcpyDeviceToHost, a.stream);
+      if (stream_wait(a) != cudaSuccess) return -1;
+      if (!a.ctl_host->any_sweep) break;
+    }
+  }
+  size_t dyn = sizeof(double) * g.p_pad + sizeof(int) * (size_t)keep + 16;
+  svd_extract_kernel<<<a.nb, 1024, dyn, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, work, US, Vh, g, (int)keep, nr_bulk,
+                                                     slot_lognorm, slot_trunc, a.mask, a.mask_want);
+  ++*a.launches;
+  phase_fix(a, Vh, US, m, n, keep, 1);
+  return sweeps;
+}
+
+// A matrix with a short side p <= 128 that does not fit the in-shared-memory kernel as a whole (64 x 512 at D = 4): one
+// Householder factorisation reduces it to p x p, which does.   wide:  A^H = Q R  ->  A = R^H Q^H,  R^H = US_s Vh_s,
+// US = US_s, Vh = Vh_s Q^H;   tall:  A = Q R,  R = US_s Vh,  US = Q US_s.  Same singular values, same truncation.
+static void svd_reduced(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep, int nr_bulk,
+                        int slot_lognorm, int slot_trunc) {
+  const int64_t p = m < n ? m : n, q = m < n ? n : m;
+  int64_t o = work;
+  const int64_t T = o; o += round_up(q * p, 8);          // A^H (wide) / unused (tall)
+  const int64_t Q = o; o += round_up(q * p, 8);
+  const int64_t R = o; o += round_up(p * p, 8);
+  const int64_t L = o; o += round_up(p * p, 8);
+  const int64_t S = o; o += round_up(p * keep, 8);       // small factor that still has to be multiplied by Q
+  const int64_t qw = o;                                  // QR workspace: q*p + q*p + p + 8
+  if (m < n) {
+    const int64_t dims[2] = {m, n}, perm[2] = {1, 0};
+    permute(a, T, A, 1, 2, dims, perm);                  // A^H, n x m
+    qr(a, T, Q, R, qw, n, m);
+    const int64_t dr[2] = {m, m};
+    permute(a, L, R, 1, 2, dr, perm);                    // R^H, m x m
+    svd_small(a, L, m, US, S, m, m, keep, nr_bulk, slot_lognorm, slot_trunc);      // S = Vh_s (keep x m)
+    gemm(a, Vh, S, Q, keep, n, m, OP_N, OP_C);           // Vh = Vh_s Q^H
+  } else {
+    qr(a, A, Q, R, qw, m, n);
+    svd_small(a, R, n, S, Vh, n, n, keep, nr_bulk, slot_lognorm, slot_trunc);      // S = US_s (n x keep)
+    gemm(a, US, Q, S, m, keep, n, OP_N, OP_N);           // US = Q US_s
+  }
+  phase_fix(a, Vh, US, m, n, keep, 1);
+}
+
+bool svd_reducible(int64_t m, int64_t n) {
+  const int64_t p = m < n ? m : n;
+  return p <= 128 && !svd_small_fits(m, n) && svd_small_fits(p, p);
+}
+
+// Dispatcher: in-smem Jacobi for small matrices, Householder reduction + in-smem Jacobi for short-and-wide ones, subspace
+// iteration when only a small leading part is kept, block-Jacobi otherwise / as the exact path of the subspace iteration.
+// host counters: [1] small, [8..] none; everything decided on the device is counted there (SvdCtl::counters).
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                 int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm) {
+                 int nr_bulk, int slot_lognorm, int slot_trunc) {
   if (m == 0 || n == 0) return 0;
   static const int force = getenv("KBP_SVD_FORCE") ? atoi(getenv("KBP_SVD_FORCE")) : 0;   // 1: block-Jacobi only, 2: no small kernel
   if (force != 1) {
@@ -446,79 +581,21 @@ int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work
       ++a.counters[1];
       return 1;
     }
-    const int b = tsvd_block(m, n, keep);
-    if (b > 0) {
-      const int r = svd_truncate_subspace(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, b, warm);
-      if (r != 0) {
-        if (r > 0) { ++a.counters[2]; a.counters[5] += r; }
-        return r;
-      }
-      ++a.counters[3];
+    if (force != 2 && svd_reducible(m, n)) {
+      svd_reduced(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
+      ++a.counters[0];
+      return 1;
     }
+    const int b = tsvd_block(m, n, keep);
+    if (b > 0) return svd_truncate_subspace(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc, b);
   }
-  ++a.counters[4];
-  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  if (debug) fprintf(stderr, "[kbp svd %lldx%lld keep %lld] block-Jacobi path\n", (long long)m, (long long)n, (long long)keep);
-  const int r = svd_truncate_jacobi(a, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
-  phase_fix(a, Vh, US, m, n, keep, 1);
-  return r;
+  Arena all = a;
+  all.mask = nullptr;
+  return svd_exact(all, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
 }
 
-static int svd_truncate_jacobi(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                               int nr_bulk, int slot_lognorm, int slot_trunc) {
-  SvdGeom g = svd_geom(m, n);
-  {
-    long long total = (long long)g.p_pad * g.ld;
-    int gx = (int)((total + 255) / 256);
-    if (gx > 148 * 8) gx = 148 * 8;
-    svd_init_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, A, work, g);
-    ++*a.launches;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(svd_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_ROUND_SMEM);
-    attr_set = true;
-  }
-  double* off0 = a.svd_off;
-  double* off1 = a.svd_off + a.nb;
-  double* fro2 = a.svd_off + 2 * a.nb;
-  svd_fro_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, m * n, fro2);
-  ++*a.launches;
-  fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(off1, a.nb, 1e300);   // "previous sweep" of sweep 0: not converged
-  ++*a.launches;
-  int sweeps = 0;
-  bool converged = false;
-  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  static const int inner_max = getenv("KBP_SVD_INNER") ? atoi(getenv("KBP_SVD_INNER")) : 2;
-  for (int s = 0; s < SVD_MAX_SWEEPS; ++s) {
-    double* cur = (s & 1) ? off1 : off0;
-    double* prev = (s & 1) ? off0 : off1;
-    cudaMemsetAsync(cur, 0, sizeof(double) * a.nb, a.stream);
-    for (int r = 0; r < g.nblk - 1; ++r) {
-      svd_round_kernel<<<dim3(g.nblk / 2, a.nb), 256, SVD_ROUND_SMEM, a.stream>>>(a.base, a.chain_stride, work, g, r, SVD_TOL, prev, cur, fro2, s < 24 ? inner_max : 15);
-      ++*a.launches;
-    }
-    cudaMemcpyAsync(a.svd_off_host, cur, sizeof(double) * a.nb, cudaMemcpyDeviceToHost, a.stream);
-    if (stream_wait(a) != cudaSuccess) return -1;
-    ++sweeps;
-    if (debug) {
-      fprintf(stderr, "[kbp svd %lldx%lld] sweep %d off:", (long long)m, (long long)n, s);
-      for (int c = 0; c < a.nb; ++c) fprintf(stderr, " %.3e", a.svd_off_host[c]);
-      fprintf(stderr, "\n");
-    }
-    double mx = 0.0;
-    for (int c = 0; c < a.nb; ++c) {
-      double v = a.svd_off_host[c];
-      if (!(v == v)) return -2;   // NaN
-      if (v > mx) mx = v;
-    }
-    if (mx < SVD_TOL) { converged = true; break; }
-  }
-  size_t dyn = sizeof(double) * g.p_pad + sizeof(int) * (size_t)keep + 16;
-  svd_extract_kernel<<<a.nb, 1024, dyn, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, work, US, Vh, g, (int)keep, nr_bulk,
-                                                     slot_lognorm, slot_trunc);
-  ++*a.launches;
-  return converged ? sweeps : -3;
+void init_svd_attributes() {
+  cudaFuncSetAttribute(svd_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SVD_ROUND_SMEM);
 }
 
 }  // namespace kbp

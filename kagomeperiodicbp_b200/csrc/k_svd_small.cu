@@ -97,6 +97,8 @@ struct SmallArgs {
   int m, n, lda, keep;
   int nr_bulk, slot_lognorm, slot_trunc;
   int group;                // lanes per row pair
+  const int* mask;          // per-chain predicate (kbp_ops.cuh: Arena::mask)
+  int mask_want;
 };
 
 size_t svd_small_smem(int64_t m, int64_t n) {
@@ -149,6 +151,7 @@ __device__ __forceinline__ void jacobi_pair_cached(cplx* __restrict__ xi, cplx* 
 template <bool CACHED, int G>
 __global__ void __launch_bounds__(CACHED ? 768 : 1024) svd_small_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
                                                                         int n_slots, SmallArgs g) {
+  if (g.mask && g.mask[blockIdx.y] != g.mask_want) return;
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int m = g.m, n = g.n;
   const bool mode_t = m > n;
@@ -349,6 +352,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 template <int CPL, int G>
 __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots,
                                                            int n_slots, SmallArgs g) {
+  if (g.mask && g.mask[blockIdx.y] != g.mask_want) return;
   constexpr int C = CL_C;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -578,11 +582,6 @@ __global__ void __launch_bounds__(1024) svd_cluster_kernel(cplx* __restrict__ ba
 
 template <int CPL, int G>
 static cudaError_t launch_cluster(const Arena& a, const SmallArgs& g, int C, int threads, size_t smem) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(svd_cluster_kernel<CPL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    attr_set = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)C, (unsigned)a.nb);
   cfg.blockDim = dim3((unsigned)threads);
@@ -600,17 +599,8 @@ static cudaError_t launch_cluster(const Arena& a, const SmallArgs& g, int C, int
 
 void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
                int slot_lognorm, int slot_trunc) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(svd_small_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    cudaFuncSetAttribute(svd_small_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
-    attr_set = true;
-  }
   SmallArgs g;
+  g.mask = a.mask; g.mask_want = a.mask_want;
   g.A = A; g.US = US; g.Vh = Vh; g.m = (int)m; g.n = (int)n; g.lda = (int)lda; g.keep = (int)keep;
   g.nr_bulk = nr_bulk; g.slot_lognorm = slot_lognorm; g.slot_trunc = slot_trunc;
   const int p = (int)(m < n ? m : n), pp = (p + 1) & ~1, npairs = pp / 2 > 0 ? pp / 2 : 1;
@@ -651,6 +641,21 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
   else { if (cached) KBP_SMALL_LAUNCH(true, 8); else KBP_SMALL_LAUNCH(false, 8); }
 #undef KBP_SMALL_LAUNCH
   ++*a.launches;
+}
+
+void init_svd_small_attributes() {
+  cudaFuncSetAttribute(svd_small_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_small_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_small_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_small_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_small_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_small_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
+  cudaFuncSetAttribute(svd_cluster_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM_MAX);
 }
 
 }  // namespace kbp

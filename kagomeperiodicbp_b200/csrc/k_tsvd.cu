@@ -128,7 +128,9 @@ __global__ void tsvd_randq_kernel(cplx* __restrict__ base, long long chain_strid
 constexpr int CNB = 16;
 
 __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
-                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat) {
+                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat, const int* __restrict__ mask,
+                                                    int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   extern __shared__ __align__(16) unsigned char ch_raw[];
   const int ld = b + 1;                                            // odd row stride: the 16 rows of a panel fall into different banks
   cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x ld
@@ -320,7 +322,8 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
 // One CTA per 32 rows, thread (row, c): the 16 threads of a row sit in one half warp, so the panel loop needs warp-level
 // synchronisation only.  The X_pp and the solved entries live in shared memory, R is read through L2.
 __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
-                                                   long long Out_, int rows, int b) {
+                                                   long long Out_, int rows, int b, const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
   extern __shared__ __align__(16) unsigned char tr_raw[];
   const int nblk = (b + CNB - 1) / CNB;
   cplx* Xs = reinterpret_cast<cplx*>(tr_raw);                     // nblk x 16 x 16: inverses of the diagonal blocks
@@ -391,7 +394,9 @@ constexpr int NPART = 32;
 constexpr int PART_STRIDE = 160;     // doubles per (chain, part): keep <= 128 row sums + 2 norms
 
 __global__ void __launch_bounds__(256) tsvd_check1_kernel(const cplx* __restrict__ base, long long chain_stride, long long C_, long long TV_,
-                                                          long long A_, long long P_, int m, int n, int keep, double* __restrict__ part) {
+                                                          long long A_, long long P_, int m, int n, int keep, double* __restrict__ part,
+                                                          const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
   __shared__ double red[34];
   const cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* C = cb + C_;
@@ -428,7 +433,9 @@ __global__ void __launch_bounds__(256) tsvd_check1_kernel(const cplx* __restrict
 
 __global__ void __launch_bounds__(128) tsvd_check2_kernel(const cplx* __restrict__ base, long long chain_stride, long long T_, int keep,
                                                           const double* __restrict__ part, double* __restrict__ resid, double* __restrict__ ratio,
-                                                          double* __restrict__ discfrac, double* __restrict__ norms) {
+                                                          double* __restrict__ discfrac, double* __restrict__ norms, const int* __restrict__ mask,
+                                                          int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   __shared__ double s2[128], r2[128];
   __shared__ double sh[2];
   const cplx* T = base + (long long)blockIdx.x * chain_stride + T_;
@@ -466,7 +473,8 @@ __global__ void __launch_bounds__(128) tsvd_check2_kernel(const cplx* __restrict
 // One CTA per chain: scale US by 1 / ||A||_F (nr_bulk) and update the slots from the norms check2 left behind.
 __global__ void __launch_bounds__(1024) tsvd_finalize_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots, int n_slots,
                                                              long long US_, long long mk, int nr_bulk, int slot_lognorm, int slot_trunc,
-                                                             const double* __restrict__ norms) {
+                                                             const double* __restrict__ norms, const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   cplx* US = base + (long long)blockIdx.x * chain_stride + US_;
   const double fro2 = norms[2 * blockIdx.x], disc = norms[2 * blockIdx.x + 1];
   const double frob = sqrt(fro2);
@@ -487,7 +495,8 @@ __global__ void __launch_bounds__(1024) tsvd_finalize_kernel(cplx* __restrict__ 
 // the next BP iteration are then continuous functions of the messages, which is what lets the subspace iteration be
 // warm-started from the previous run's Ritz basis.  One CTA per chain, one warp per row.
 __global__ void __launch_bounds__(1024) phase_fix_kernel(cplx* __restrict__ base, long long chain_stride, long long Vh_, long long US_, int m, int n,
-                                                         int keep, int us_too) {
+                                                         int keep, int us_too, const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   cplx* Vh = base + (long long)blockIdx.x * chain_stride + Vh_;
   cplx* US = base + (long long)blockIdx.x * chain_stride + US_;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(1024) phase_fix_kernel(cplx* __restrict__ base
 }
 
 void phase_fix(const Arena& a, int64_t Vh, int64_t US, int64_t m, int64_t n, int64_t keep, int us_too) {
-  phase_fix_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, Vh, US, (int)m, (int)n, (int)keep, us_too);
+  phase_fix_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, Vh, US, (int)m, (int)n, (int)keep, us_too, a.mask, a.mask_want);
   ++*a.launches;
 }
 
@@ -538,266 +547,309 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
   PM(1);
   const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 3 * sizeof(double) * (size_t)b + 32;
   const int64_t Xd = Dinv + b;                                     // diagonal-block inverses behind the 1/diagonal entries
-  chol_kernel<<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat);
+  chol_kernel<<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat, a.mask, a.mask_want);
   ++*a.launches;
   PM(2);
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
     const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17 +
                                             (size_t)CNB * CNB * (nblk * (nblk - 1) / 2)) + 32;
-    trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b);
+    trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b, a.mask, a.mask_want);
     ++*a.launches;
     PM(3);
   }
   return T;
 }
 
-// returns iterations used (> 0) on success, 0 if the caller must fall back to the full Jacobi SVD, < 0 on CUDA failure
-//
-// Two kinds of iteration.  SAFE (cold start, Q arbitrary): W = A Q, Y = orth(W), Z = A^H Y, Q = orth(Z).  FAST (Q holds
-// approximate Ritz vectors in decreasing order -- after the first Rayleigh-Ritz step, or from the previous run of the same
-// op): the columns of A Q and of A^H A Q are then nearly orthogonal, their Gram matrices are diagonally dominant after
-// scaling, and ONE Cholesky-QR of Z = A^H (A Q) per iteration is as accurate as the safe sequence (the Cholesky kernel
-// reports its smallest pivot / diagonal; a result built on a pivot ratio below TSVD_PIVOT_TRUST is not accepted).
+// ------------------------------------------------------------------------------------------------
+// The decision after every Rayleigh-Ritz round, on the device (one thread): per chain accept / iterate further / exact path.
+// A chain that is done leaves the RUNNING state, which is the per-chain predicate of every launch of the following rounds.
+//   accept    residual <= TSVD_RES_TOL, Cholesky pivots of the round trustworthy, no collapse of the kept spectrum
+//   exact     kept spectrum collapses with measurable discarded weight, non-finite flags, or the round budget is spent
 constexpr double TSVD_PIVOT_TRUST = 1e-3;
 
-int svd_truncate_subspace(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                          int nr_bulk, int slot_lognorm, int slot_trunc, int b, int64_t warm) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-    attr_set = true;
+__global__ void tsvd_decide_kernel(SvdCtl* __restrict__ ctl, int* __restrict__ state, double* __restrict__ stat, const double* __restrict__ resid,
+                                   const double* __restrict__ ratio, const double* __restrict__ discf, int nb, int first, int max_rounds,
+                                   int iters_first, int iters_more, cudaGraphConditionalHandle h_loop, cudaGraphConditionalHandle h_exact,
+                                   int use_handles) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int round = first ? 1 : ctl->round + 1;
+  int any_run = 0, any_exact = 0;
+  for (int c = 0; c < nb; ++c) {
+    int st = first ? CHAIN_RUNNING : state[c];
+    if (st == CHAIN_RUNNING) {
+      const double pv = stat[c], rs = resid[c], ra = ratio[c], df = discf[c];
+      const bool finite = pv == pv && rs == rs && ra == ra && df == df;
+      const bool trusted = pv >= TSVD_PIVOT_TRUST;
+      const bool collapse = trusted && ra < TSVD_MIN_RATIO && df > 1e-24;
+      if (finite && trusted && !collapse && rs <= TSVD_RES_TOL) {
+        st = CHAIN_ACCEPTED;
+        ctl->counters[2] += 1;
+        ctl->counters[5] += iters_first + (long long)(round - 1) * iters_more;
+      } else if (!finite || collapse || round >= max_rounds) {
+        st = CHAIN_EXACT;
+        ctl->counters[3] += 1;
+      }
+    }
+    state[c] = st;
+    stat[c] = 1.0;                               // smallest Cholesky pivot ratio of the next round
+    any_run |= st == CHAIN_RUNNING;
+    any_exact |= st == CHAIN_EXACT;
   }
-  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
-  static const int it_warm = getenv("KBP_TSVD_ITWARM") ? atoi(getenv("KBP_TSVD_ITWARM")) : 2;
-  static const int it_step = getenv("KBP_TSVD_ITSTEP") ? atoi(getenv("KBP_TSVD_ITSTEP")) : 3;
-  // cold start: after `safe0` SAFE iterations the block is already ordered well enough (contamination of column j by a
-  // larger direction i has decayed as (s_j/s_i)^(2k), one fast step amplifies it by (s_i/s_j)^2) for the FAST form
-  static const int safe0 = getenv("KBP_TSVD_SAFE0") ? atoi(getenv("KBP_TSVD_SAFE0")) : 2;
-  // a block narrower than 2.5 keep (shared-memory cap of the b x b kernels, e.g. D = 6: keep 72, b 112) converges more slowly:
-  // more iterations are still far cheaper than the exact path on a (chi D^2)^2 matrix
-  static const int it_max_env = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 0;
-  const int it_max = it_max_env > 0 ? it_max_env : (2 * b >= 5 * keep ? 24 : 72);
-  // warm start from the previous run's Ritz basis is opt-in: across BP iterations the message tensors keep changing gauge
-  // in their (physically irrelevant) near-null directions, which makes the stored basis stale more often than not
-  static const bool no_warm = getenv("KBP_TSVD_WARM") == nullptr || atoi(getenv("KBP_TSVD_WARM")) == 0;
-  const int64_t q = m < n ? n : m, qp = rup8(q), bb = (int64_t)b * b;
-  // workspace carve-up (complex128 elements)
-  int64_t o = work;
-  int64_t buf[4];                     // four q x b panels: Q, W, scratch, check product
-  for (int i = 0; i < 4; ++i) { buf[i] = o; o += qp * b; }
-  const int64_t Gp = o; o += GRAM_SPLIT * bb;
-  const int64_t Ri = o; o += bb;      // 1 / diagonal of the last Cholesky factor (b entries)
-  const int64_t Rs = o; o += bb;      // the last Cholesky factor when the caller does not keep it
-  const int64_t R1 = o; o += bb;
-  const int64_t R2 = o; o += bb;
-  const int64_t Rm = o; o += bb;
-  const int64_t USs = o; o += bb;    // b x b (unused output of the small SVD)
-  const int64_t Vbs = o; o += bb;    // b x b: all Ritz vectors, rows sorted by singular value
-  const int64_t Tk = o; o += bb;     // keep x keep
-  const int64_t Pb = o;              // m x n: P = US Vh
-  double* stat = a.svd_off;          // [nb] min pivot ratio
+  ctl->round = round;
+  ctl->any_run = any_run;
+  ctl->any_exact = any_exact;
+  if (use_handles) {
+    cudaGraphSetConditional(h_loop, any_run ? 1u : 0u);
+    cudaGraphSetConditional(h_exact, any_exact ? 1u : 0u);
+  }
+}
+
+int svd_exact(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep, int nr_bulk,
+              int slot_lognorm, int slot_trunc);
+
+// ---- conditional graph nodes ------------------------------------------------------------------------------------------
+cudaGraphConditionalHandle new_cond_handle(const Arena& a) {
+  cudaGraphConditionalHandle h = 0;
+  if (a.capture) cudaGraphConditionalHandleCreate(&h, a.top_graph, 0, cudaGraphCondAssignDefault);
+  return h;
+}
+
+bool begin_cond_body(const Arena& a, cudaGraphConditionalHandle h, bool is_while, Arena* body) {
+  cudaStreamCaptureStatus st;
+  unsigned long long id;
+  cudaGraph_t g = nullptr;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  if (a.depth >= 2) return false;
+  if (cudaStreamGetCaptureInfo_v2(a.stream, &st, &id, &g, &deps, &nd) != cudaSuccess || st != cudaStreamCaptureStatusActive) return false;
+  cudaGraphNodeParams p = {};
+  p.type = cudaGraphNodeTypeConditional;
+  p.conditional.handle = h;
+  p.conditional.type = is_while ? cudaGraphCondTypeWhile : cudaGraphCondTypeIf;
+  p.conditional.size = 1;
+  cudaGraphNode_t node;
+  if (cudaGraphAddNode(&node, g, deps, nd, &p) != cudaSuccess) return false;
+  if (cudaStreamUpdateCaptureDependencies(a.stream, &node, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) return false;
+  *body = a;
+  body->stream = a.body_stream[a.depth];
+  body->depth = a.depth + 1;
+  return cudaStreamBeginCaptureToGraph(body->stream, p.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+}
+
+bool end_body(const Arena& body) {
+  cudaGraph_t g = nullptr;
+  return cudaStreamEndCapture(body.stream, &g) == cudaSuccess;
+}
+
+static cudaError_t read_ctl(const Arena& a) {
+  cudaMemcpyAsync(a.ctl_host, a.ctl, sizeof(SvdCtl), cudaMemcpyDeviceToHost, a.stream);
+  return stream_wait(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace of one subspace truncation (complex128 elements from `work`)
+struct TsvdBufs {
+  int64_t panel[4];                  // four q x b panels
+  int64_t Gp, Ri, Rs, R1, R2, Rm, Vbs, Tk, Pb;
+};
+
+// Rayleigh-Ritz on span(Q), the kept factors, and the two check kernels.  Q in panel `Qb`, `f0`, `f1` free panels.
+static void rayleigh_ritz_and_check(const Arena& a, const TsvdBufs& w, int64_t A, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep,
+                                    int b, int64_t Qb, int64_t f0, int64_t f1, bool single_pass) {
+  double* stat = a.svd_off;
   double* resid = a.svd_off + a.nb;
   double* ratio = a.svd_off + 2 * a.nb;
   double* discf = a.svd_off + 3 * a.nb;
-  double* norms = a.svd_off + 4 * a.nb;            // [2 nb]
-  double* part = a.svd_off + 6 * a.nb;             // [nb][NPART][PART_STRIDE]
-  if (keep > 128) return 0;
-
-  // panel bookkeeping: Qb = current basis, the rest are free
-  int64_t Qb, f0 = buf[1], f1 = buf[2], f2 = buf[3];
-  bool ordered = false;
-  if (warm >= 0 && !no_warm) {
-    auto it = a.warm->find((long long)warm);
-    ordered = it != a.warm->end() && it->second == b;
-  }
-  const bool is_warm = ordered;
-  // The first round of a cold start (pseudo-random block, a fixed number of iterations, Rayleigh-Ritz, copy of the flags) is
-  // a constant launch sequence for a given op of a given program: captured into a CUDA graph on its second execution and
-  // replayed afterwards (~70 launches -> one).  Everything that depends on the flags stays on the plain path.
-  static const bool graphs_on = graphs_enabled();
-  TsvdGraph* tg = nullptr;
-  bool replayed = false, capturing = false;
-  if (graphs_on && !is_warm && !debug && a.tsvd_graphs) {
-    unsigned long long h = 1469598103934665603ull;
-    const long long keyv[10] = {(long long)A, (long long)US, (long long)Vh, (long long)work, (long long)m, (long long)n, (long long)keep,
-                                b, nr_bulk * 4096 + (slot_lognorm + 1) * 64 + (slot_trunc + 1), it_cold};
-    for (int i = 0; i < 10; ++i) { h ^= (unsigned long long)keyv[i]; h *= 1099511628211ull; }
-    if (a.tsvd_graphs->size() < 4096 || a.tsvd_graphs->count(h)) {
-      tg = &(*a.tsvd_graphs)[h];
-      if (tg->exec) replayed = true;
-      else if (!tg->bad && tg->seen++ >= 1) capturing = cudaStreamBeginCapture(a.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    }
-  }
-  const int64_t launches_before = *a.launches;
-  PM(7);
-  if (ordered) {
-    Qb = warm;                       // Ritz basis of the previous run of this op (n x b, orthonormal columns); read only
+  double* norms = a.svd_off + 4 * a.nb;
+  double* part = a.svd_off + 6 * a.nb;
+  gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q -> f0
+  PM(0);
+  int64_t Rsmall;
+  if (single_pass) {
+    cholqr_pass(a, f0, -1, w.Gp, w.Ri, w.R1, m, b, stat);           // W = Y R1
+    Rsmall = w.R1;
   } else {
-    Qb = buf[0];
-    if (!replayed) {
-      const long long total = (long long)n * b;
-      int gx = (int)((total + 255) / 256);
-      if (gx > 148 * 4) gx = 148 * 4;
-      tsvd_randq_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, Qb, total);
-      ++*a.launches;
-    }
+    cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.R1, m, b, stat);
+    cholqr_pass(a, f1, -1, w.Gp, w.Ri, w.R2, m, b, stat);
+    gemm(a, w.Rm, w.R2, w.R1, b, b, b, OP_N, OP_N);                 // W = Y (R2 R1)
+    PM(5);
+    Rsmall = w.Rm;
   }
-  // after `Qb = newbuf`, the old basis panel becomes free unless it is the persistent warm buffer
+  svd_small(a, Rsmall, b, -1, w.Vbs, b, b, b, 0, -1, -1);           // Vbs = Vb^H (b x b), rows by decreasing singular value
+  PM(4);
+  gemm(a, Vh, w.Vbs, Qb, keep, n, b, OP_N, OP_C);                   // Vh = Vb_k^H Q^H
+  phase_fix(a, Vh, US, m, n, keep, 0);                              // canonical gauge of the kept bond
+  gemm(a, US, A, Vh, m, keep, n, OP_N, OP_C);                       // US = A Vh^H
+  gemm(a, f0, US, A, keep, n, m, OP_C, OP_N);                       // C = US^H A        -> f0
+  gemm(a, w.Tk, f0, Vh, keep, keep, n, OP_N, OP_C);                 // T = C Vh^H
+  gemm(a, f1, w.Tk, Vh, keep, n, keep, OP_N, OP_N);                 // TV = T Vh         -> f1
+  gemm(a, w.Pb, US, Vh, m, n, keep, OP_N, OP_N);                    // P = US Vh
+  PM(5);
+  tsvd_check1_kernel<<<dim3(NPART, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, f0, f1, A, w.Pb, (int)m, (int)n, (int)keep, part, a.mask, a.mask_want);
+  tsvd_check2_kernel<<<a.nb, 128, 0, a.stream>>>(a.base, a.chain_stride, w.Tk, (int)keep, part, resid, ratio, discf, norms, a.mask, a.mask_want);
+  *a.launches += 2;
+  PM(6);
+}
+
+// One more round from the Ritz basis of the previous one: `TSVD_IT_MORE` FAST iterations (an odd number: Q ends in the panel
+// it started in, so the round is a loop body with fixed buffer roles), Rayleigh-Ritz, check, decision.
+constexpr int TSVD_IT_MORE = 3;
+
+static void tsvd_more_round(const Arena& a, const TsvdBufs& w, int64_t A, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int b,
+                            int64_t Qb, int64_t f0, int64_t f1, int64_t f2, int max_rounds, int iters_first,
+                            cudaGraphConditionalHandle h_loop, cudaGraphConditionalHandle h_exact) {
+  double* stat = a.svd_off;
+  gemm(a, f2, Qb, w.Vbs, n, b, b, OP_N, OP_C);                      // Ritz vectors Q Vb, ordered         -> f2
+  PM(5);
+  int64_t cur = f2, other = Qb;
+  for (int it = 0; it < TSVD_IT_MORE; ++it) {
+    gemm(a, f0, A, cur, m, b, n, OP_N, OP_N);                       // W = A Q
+    gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                        // Z = A^H W
+    PM(0);
+    cholqr_pass(a, f1, other, w.Gp, w.Ri, w.Rs, n, b, stat);        // Q = orth(Z) -> other
+    const int64_t t = cur; cur = other; other = t;
+  }
+  // TSVD_IT_MORE odd: cur == Qb again
+  rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, cur, f0, f1, true);
+  tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 0,
+                                             max_rounds, iters_first, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0);
+  ++*a.launches;
+}
+
+// Two kinds of iteration.  SAFE (cold start, Q arbitrary): W = A Q, Y = orth(W), Z = A^H Y, Q = orth(Z).  FAST (Q holds
+// approximate Ritz vectors in decreasing order -- after `safe0` SAFE iterations of a cold start, or after a Rayleigh-Ritz
+// step): the columns of A Q and of A^H A Q are then nearly orthogonal, their Gram matrices are diagonally dominant after
+// scaling, and ONE Cholesky-QR of Z = A^H (A Q) per iteration is as accurate as the safe sequence (the Cholesky kernel
+// reports its smallest pivot / diagonal; a round built on a pivot ratio below TSVD_PIVOT_TRUST is not accepted).
+//
+// No host decision anywhere: round 1 is a fixed launch sequence, every further round is the body of a WHILE node (graph
+// mode) or of a host loop reading the device's control block (host-driven mode), the exact path is an IF node.
+// Returns the number of launches-visible rounds (>= 1), < 0 on a CUDA failure.
+int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
+                          int nr_bulk, int slot_lognorm, int slot_trunc, int b) {
+  static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
+  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
+  // cold start: after `safe0` SAFE iterations the block is already ordered well enough (contamination of column j by a
+  // larger direction i has decayed as (s_j/s_i)^(2k), one fast step amplifies it by (s_i/s_j)^2) for the FAST form
+  static const int safe0 = getenv("KBP_TSVD_SAFE0") ? atoi(getenv("KBP_TSVD_SAFE0")) : 2;
+  // a block narrower than 2.5 keep converges more slowly: more iterations are still far cheaper than the exact path
+  static const int it_max_env = getenv("KBP_TSVD_ITMAX") ? atoi(getenv("KBP_TSVD_ITMAX")) : 0;
+  const int it_max = it_max_env > 0 ? it_max_env : (2 * b >= 5 * keep ? 24 : 72);
+  const int max_rounds = 1 + (it_max > it_cold ? (it_max - it_cold + TSVD_IT_MORE - 1) / TSVD_IT_MORE : 0);
+  if (keep > 128) return svd_exact(a0, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
+  Arena a = a0;
+  a.mask = nullptr;
+  const int64_t q = m < n ? n : m, qp = rup8(q), bb = (int64_t)b * b;
+  TsvdBufs w;
+  int64_t o = work;
+  for (int i = 0; i < 4; ++i) { w.panel[i] = o; o += qp * b; }
+  w.Gp = o; o += GRAM_SPLIT * bb;
+  w.Ri = o; o += bb;      // 1 / diagonal of the last Cholesky factor (b entries) + the inverses of its diagonal blocks
+  w.Rs = o; o += bb;      // the last Cholesky factor when the caller does not keep it
+  w.R1 = o; o += bb;
+  w.R2 = o; o += bb;
+  w.Rm = o; o += bb;
+  w.Vbs = o; o += 2 * bb; // b x b: all Ritz vectors, rows sorted by singular value
+  w.Tk = o; o += bb;      // keep x keep
+  w.Pb = o;               // m x n: P = US Vh
+  double* stat = a.svd_off;          // [nb] min pivot ratio, then [nb] each: residual, ratio, discarded fraction, [2 nb] norms, partial sums
+  double* norms = a.svd_off + 4 * a.nb;
+  const cudaGraphConditionalHandle h_loop = new_cond_handle(a), h_exact = new_cond_handle(a);
+
+  // ---- round 1: pseudo-random block, it_cold iterations
+  int64_t Qb = w.panel[0], f0 = w.panel[1], f1 = w.panel[2], f2 = w.panel[3];
+  PM(7);
+  {
+    const long long total = (long long)n * b;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 148 * 4) gx = 148 * 4;
+    tsvd_randq_kernel<<<dim3(gx, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, Qb, total);
+    tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
+    *a.launches += 2;
+  }
   auto replace_q = [&](int64_t nq) {
     const int64_t old = Qb;
     Qb = nq;
     if (nq == f0) f0 = old; else if (nq == f1) f1 = old; else f2 = old;
-    if (old == warm) { if (f0 == warm) f0 = buf[0]; else if (f1 == warm) f1 = buf[0]; else if (f2 == warm) f2 = buf[0]; }
   };
-  // per-op schedule: the same truncation of the same program (next BP iteration: nearly the same spectrum) remembers after
-  // how many iterations its check passed -- first check there next time instead of at the fixed default
-  static const bool adaptive = getenv("KBP_TSVD_ADAPT") && atoi(getenv("KBP_TSVD_ADAPT")) != 0;   // opt-in: measured neutral
-  const long long sched_key = (long long)A * 4096 + (m % 64) * 64 + (n % 64);
-  int first = ordered ? it_warm : it_cold;
-  if (adaptive && !ordered) {
-    auto it = a.sched->find(sched_key);
-    if (it != a.sched->end()) first = it->second;
-  }
-  bool allow_cold_fast = true;
-  int done = 0, target = first;
-  if (target < 1) target = 1;
-  int checks = 0;
-  while (true) {
-    const bool rr_ordered = ordered;
-    bool cold_fast = false;
-    if (replayed && checks == 0) {
-      cold_fast = tg->cold_fast;
-      if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
-      Qb = tg->Qb; f0 = tg->f0; f1 = tg->f1; f2 = tg->f2; done = tg->done;
-      *a.launches += tg->launches;
+  bool cold_fast = false;
+  for (int done = 0; done < it_cold; ++done) {
+    gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q          -> f0
+    PM(0);
+    if (done >= safe0) {
+      if (!cold_fast) {                                               // pivots of the SAFE start say nothing about the FAST steps
+        tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
+        ++*a.launches;
+        cold_fast = true;
+      }
+      gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                        // Z = A^H W        -> f1
+      PM(0);
+      cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat);           // orth(Z)          -> f0
+      if (done + 1 == it_cold) { cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat); replace_q(f1); }   // twice on the last one
+      else replace_q(f0);
     } else {
+      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, m, b, stat);           // Y = orth(W)      -> f1
+      gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                        // Z = A^H Y        -> f0
+      PM(0);
+      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat);           // orth(Z)          -> f1
+      if (done + 1 == it_cold) { cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat); replace_q(f0); }   // twice on the last one
+      else replace_q(f1);
+    }
+  }
+  if (!cold_fast) {                                                   // all-SAFE schedule: its pivots are not a trust criterion
     tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
     ++*a.launches;
-    for (; done < target; ++done) {
-      gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                        // W = A Q          -> f0
-      PM(0);
-      if (!ordered && allow_cold_fast && done >= safe0) {
-        if (!cold_fast) {                                             // pivots of the SAFE start say nothing about the FAST steps
-          tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
-          ++*a.launches;
-          cold_fast = true;
-        }
-        gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
-        PM(0);
-        cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f0
-        if (done + 1 == target) { cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat); replace_q(f1); }   // twice on the last one
-        else replace_q(f0);
-      } else if (!ordered) {
-        cholqr_pass(a, f0, f1, Gp, Ri, Rs, m, b, stat);               // Y = orth(W)      -> f1
-        gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                      // Z = A^H Y        -> f0
-        PM(0);
-        cholqr_pass(a, f0, f1, Gp, Ri, Rs, n, b, stat);               // orth(Z)          -> f1
-        if (done + 1 == target) { cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat); replace_q(f0); }   // twice on the last one
-        else replace_q(f1);
-      } else {
-        gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                      // Z = A^H W        -> f1
-        PM(0);
-        cholqr_pass(a, f1, f0, Gp, Ri, Rs, n, b, stat);               // Q = orth(Z)      -> f0
-        replace_q(f0);
-      }
-    }
-    // ---- Rayleigh-Ritz on span(Q)
-    gemm(a, f0, A, Qb, m, b, n, OP_N, OP_N);                          // W = A Q -> f0
-    PM(0);
-    int64_t Rsmall;
-    static const bool rr_single = !(getenv("KBP_TSVD_RR_SINGLE") && atoi(getenv("KBP_TSVD_RR_SINGLE")) == 0);
-    if (rr_ordered || (cold_fast && rr_single)) {
-      cholqr_pass(a, f0, -1, Gp, Ri, R1, m, b, stat);                 // W = Y R1
-      Rsmall = R1;
-    } else {
-      cholqr_pass(a, f0, f1, Gp, Ri, R1, m, b, stat);
-      cholqr_pass(a, f1, -1, Gp, Ri, R2, m, b, stat);
-      gemm(a, Rm, R2, R1, b, b, b, OP_N, OP_N);                       // W = Y (R2 R1)
-      PM(5);
-      Rsmall = Rm;
-    }
-    svd_small(a, Rsmall, b, -1, Vbs, b, b, b, 0, -1, -1);             // Vbs = Vb^H (b x b), rows by decreasing singular value
-    PM(4);
-    gemm(a, Vh, Vbs, Qb, keep, n, b, OP_N, OP_C);                     // Vh = Vb_k^H Q^H
-    phase_fix(a, Vh, US, m, n, keep, 0);                              // canonical gauge of the kept bond
-    gemm(a, US, A, Vh, m, keep, n, OP_N, OP_C);                       // US = A Vh^H
-    gemm(a, f0, US, A, keep, n, m, OP_C, OP_N);                       // C = US^H A        -> f0
-    gemm(a, Tk, f0, Vh, keep, keep, n, OP_N, OP_C);                   // T = C Vh^H
-    gemm(a, f1, Tk, Vh, keep, n, keep, OP_N, OP_N);                   // TV = T Vh         -> f1
-    gemm(a, Pb, US, Vh, m, n, keep, OP_N, OP_N);                      // P = US Vh
-    PM(5);
-    tsvd_check1_kernel<<<dim3(NPART, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, f0, f1, A, Pb, (int)m, (int)n, (int)keep, part);
-    tsvd_check2_kernel<<<a.nb, 128, 0, a.stream>>>(a.base, a.chain_stride, Tk, (int)keep, part, resid, ratio, discf, norms);
-    *a.launches += 2;
-    // one host round trip: [stat | resid | ratio | discfrac] are contiguous in svd_off
-    cudaMemcpyAsync(a.svd_off_host, a.svd_off, sizeof(double) * 4 * a.nb, cudaMemcpyDeviceToHost, a.stream);
-    PM(6);
-    if (capturing && checks == 0) {
-      cudaGraph_t graph = nullptr;
-      const cudaError_t e1 = cudaStreamEndCapture(a.stream, &graph);
-      cudaError_t e2 = cudaErrorUnknown;
-      if (e1 == cudaSuccess && graph) e2 = cudaGraphInstantiate(&tg->exec, graph, 0);
-      if (graph) cudaGraphDestroy(graph);
-      if (e2 != cudaSuccess) { tg->exec = nullptr; tg->bad = true; cudaGetLastError(); return -1; }
-      tg->Qb = Qb; tg->f0 = f0; tg->f1 = f1; tg->f2 = f2; tg->done = done; tg->cold_fast = cold_fast;
-      tg->launches = *a.launches - launches_before;
-      if (cudaGraphLaunch(tg->exec, a.stream) != cudaSuccess) return -1;
-      capturing = false;
-    }
-    }
-    if (stream_wait(a) != cudaSuccess) return -1;
-    t_prof.flush();
-    PM(7);
-    double worst = 0.0, minpiv = 1.0, minratio = 1.0, maxdisc = 0.0;
-    for (int c = 0; c < a.nb; ++c) {
-      const double pv = a.svd_off_host[c], rs = a.svd_off_host[a.nb + c], ra = a.svd_off_host[2 * a.nb + c], df = a.svd_off_host[3 * a.nb + c];
-      if (!(rs == rs) || !(ra == ra) || !(df == df)) { worst = 1e300; continue; }
-      if (pv < minpiv) minpiv = pv;
-      if (rs > worst) worst = rs;
-      if (ra < minratio) minratio = ra;
-      if (df > maxdisc) maxdisc = df;
-    }
-    if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d%s%s] it %d resid %.3e s_k/s_1 %.3e min pivot %.3e disc %.3e\n", (long long)m, (long long)n,
-                       (long long)keep, b, is_warm ? " warm" : "", rr_ordered ? " fast" : (cold_fast ? " cold-fast" : ""), done, worst, minratio, minpiv, maxdisc);
-    // a spectrum that collapses inside the kept part: fine if nothing measurable is discarded (rank <= keep), else exact
-    // path.  A fast round whose Cholesky pivots were small says nothing either way: it is redone with safe iterations.
-    const bool trusted = !(rr_ordered || cold_fast) || minpiv >= TSVD_PIVOT_TRUST;
-    const bool collapse = trusted && minratio < TSVD_MIN_RATIO && maxdisc > 1e-24;
-    ++checks;
-    if (!collapse && trusted && worst <= TSVD_RES_TOL) {
-      if (adaptive && !is_warm) {
-        // passed at the first check with a residual far below the tolerance: try one iteration less next time; needed
-        // more checks: go straight to this count next time
-        int next = done;
-        if (checks == 1 && worst <= TSVD_RES_TOL * 0.03 && done > 3) next = done - 1;
-        (*a.sched)[sched_key] = next;
-      }
-      break;
-    }
-    if (collapse || done >= it_max) {
-      if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld] FALLBACK after %d iterations: resid %.3e s_k/s_1 %.3e\n", (long long)m, (long long)n, done, worst, minratio);
-      if (warm >= 0) a.warm->erase((long long)warm);
-      return 0;
-    }
-    // continue from the Ritz basis Q Vb (ordered) -- unless the fast path just proved untrustworthy
-    gemm(a, f2, Qb, Vbs, n, b, b, OP_N, OP_C);
-    PM(5);
-    replace_q(f2);
-    ordered = trusted;
-    if (!trusted) allow_cold_fast = false;
-    target = done + (done < 12 ? it_step : 2 * it_step);
-    if (target > it_max) target = it_max;
   }
-  if (warm >= 0 && !no_warm) {
-    gemm(a, warm, Qb, Vbs, n, b, b, OP_N, OP_C);                      // Ritz basis Q Vb for the next run (Qb != warm here)
-    (*a.warm)[(long long)warm] = b;
-  }
-  tsvd_finalize_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, US, m * keep, nr_bulk, slot_lognorm, slot_trunc, norms);
+  rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, Qb, f0, f1, cold_fast);
+  tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 1,
+                                             max_rounds, it_cold, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0);
   ++*a.launches;
-  return done > 0 ? done : 1;
+
+  // ---- further rounds while some chain is RUNNING; only those chains take part
+  int rounds = 1;
+  if (a.capture) {
+    Arena body;
+    if (!begin_cond_body(a, h_loop, true, &body)) return -1;
+    body.mask = a.chain_state; body.mask_want = CHAIN_RUNNING;
+    tsvd_more_round(body, w, A, US, Vh, m, n, keep, b, Qb, f0, f1, f2, max_rounds, it_cold, h_loop, h_exact);
+    if (!end_body(body)) return -1;
+  } else {
+    if (read_ctl(a) != cudaSuccess) return -1;
+    t_prof.flush();
+    Arena body = a;
+    body.mask = a.chain_state; body.mask_want = CHAIN_RUNNING;
+    while (a.ctl_host->any_run) {
+      if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d] round %d: another %d iterations\n", (long long)m, (long long)n, (long long)keep, b, rounds, TSVD_IT_MORE);
+      tsvd_more_round(body, w, A, US, Vh, m, n, keep, b, Qb, f0, f1, f2, max_rounds, it_cold, h_loop, h_exact);
+      ++rounds;
+      if (read_ctl(a) != cudaSuccess) return -1;
+      t_prof.flush();
+    }
+  }
+  // ---- accepted chains: scale US, update the slots
+  tsvd_finalize_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, US, m * keep, nr_bulk, slot_lognorm, slot_trunc, norms,
+                                                     a.chain_state, CHAIN_ACCEPTED);
+  ++*a.launches;
+  // ---- chains the iteration could not settle: exact block-Jacobi SVD of the same matrix
+  if (a.capture) {
+    Arena body;
+    if (!begin_cond_body(a, h_exact, false, &body)) return -1;
+    body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
+    const int r = svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
+    if (!end_body(body) || r < 0) return -1;
+  } else if (a.ctl_host->any_exact) {
+    if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d] exact path after %d rounds\n", (long long)m, (long long)n, (long long)keep, b, rounds);
+    Arena body = a;
+    body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
+    if (svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc) < 0) return -1;
+  }
+  return rounds;
+}
+
+void init_tsvd_attributes() {
+  cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
 }
 
 }  // namespace kbp

@@ -176,3 +176,18 @@ void count_nonfinite(const Arena& a, int64_t buf, int64_t n, int slot) {
 }
 
 }  // namespace kbp
+
+namespace kbp {
+void init_gemm_attributes();
+void init_qr_attributes();
+void init_svd_attributes();
+void init_svd_small_attributes();
+void init_tsvd_attributes();
+void init_device_attributes() {
+  init_gemm_attributes();
+  init_qr_attributes();
+  init_svd_attributes();
+  init_svd_small_attributes();
+  init_tsvd_attributes();
+}
+}  // namespace kbp

@@ -2,10 +2,12 @@
 #include "../../include/kbp.h"
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -27,14 +29,16 @@ struct kbp_ctx {
   double* svd_off = nullptr;
   double* svd_off_host = nullptr;
   int64_t launches = 0;
-  int64_t svd_sweeps = 0;
   int64_t counters[8] = {0};
-  std::unordered_map<long long, int> warm;
-  std::unordered_map<long long, int> sched;
-  std::unordered_map<unsigned long long, kbp::TsvdGraph> tsvd_graphs;
+  kbp::SvdCtl* ctl = nullptr;            // device control block of the truncation in flight, followed by int state[nb]
+  kbp::SvdCtl* ctl_host = nullptr;       // pinned mirror (host-driven mode, counters)
+  cudaStream_t body_stream[2] = {nullptr, nullptr};   // capture streams of conditional-node bodies
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; bool bad = false; };
-  std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of sync-free programs, keyed by a hash of the op stream
+  std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of whole programs, keyed by a hash of the op stream
   int64_t graph_replays = 0;
+  int64_t graph_captures = 0;
+  int64_t graph_min_words = 256;         // shorter programs (one-off algebra of the ITE step) run as plain launches
+  bool graph_first = false;              // capture a program the first time it is seen (default: the second)
   bool profile = false;
   struct Span { int op; cudaEvent_t a, b; };
   std::vector<Span> spans;
@@ -81,9 +85,18 @@ int kbp_create(int device, kbp_ctx** out) {
   kbp_ctx* c = new kbp_ctx();
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->body_stream[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->body_stream[1], cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     delete c;
     return KBP_E_CUDA;
+  }
+  {
+    // the > 48 KB shared-memory opt-in is a per-device function attribute: set once for every device a context is made on
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 64 && !done[device]) { kbp::init_device_attributes(); done[device] = true; cudaGetLastError(); }
   }
   // blocking host waits on request (KBP_BLOCKING_SYNC=1): useful when many ranks share few host cores; measured on a
   // 4 x B200 / 32-core box the default spin wait is ~6 % faster, so it stays the default
@@ -98,12 +111,18 @@ static void drop_graphs(kbp_ctx* c) {
   for (auto& kv : c->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   c->graphs.clear();
-  for (auto& kv : c->tsvd_graphs)
-    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  c->tsvd_graphs.clear();
+}
+
+static void fold_device_counters(kbp_ctx* c) {
+  if (!c->ctl || !c->ctl_host) return;
+  if (cudaMemcpyAsync(c->ctl_host, c->ctl, sizeof(kbp::SvdCtl), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return;
+  for (int k = 2; k < 8; ++k) c->counters[k] += c->ctl_host->counters[k];
+  cudaMemsetAsync(reinterpret_cast<char*>(c->ctl) + offsetof(kbp::SvdCtl, counters), 0, sizeof(long long) * 8, c->stream);
 }
 
 static void free_arena(kbp_ctx* c) {
+  fold_device_counters(c);
   drop_graphs(c);
   if (c->arena) cudaFree(c->arena);
   if (c->slots) cudaFree(c->slots);
@@ -112,6 +131,9 @@ static void free_arena(kbp_ctx* c) {
   c->scratch = nullptr; c->counters_dev = nullptr;
   if (c->svd_off) cudaFree(c->svd_off);
   if (c->svd_off_host) cudaFreeHost(c->svd_off_host);
+  if (c->ctl) cudaFree(c->ctl);
+  if (c->ctl_host) cudaFreeHost(c->ctl_host);
+  c->ctl = nullptr; c->ctl_host = nullptr;
   c->arena = nullptr; c->slots = nullptr; c->svd_off = nullptr; c->svd_off_host = nullptr;
   c->chain_elems = 0; c->nb = 0; c->n_slots = 0;
 }
@@ -125,6 +147,8 @@ void kbp_destroy(kbp_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->block_event) cudaEventDestroy(c->block_event);
   if (c->stream) cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 2; ++i)
+    if (c->body_stream[i]) cudaStreamDestroy(c->body_stream[i]);
   delete c;
 }
 
@@ -141,13 +165,15 @@ int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
     CU(c, cudaMalloc(&c->scratch, sizeof(double2) * (size_t)KBP_GEMM_SCRATCH * nb));
     CU(c, cudaMalloc(&c->counters_dev, sizeof(int) * (size_t)4096 * nb));
     CU(c, cudaMemsetAsync(c->counters_dev, 0, sizeof(int) * (size_t)4096 * nb, c->stream));
-    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)(6 + 32 * 160) * nb));
+    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)(6 + 32 * 160 + 3) * nb));
     CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * 4 * nb));
+    CU(c, cudaMalloc(&c->ctl, sizeof(kbp::SvdCtl) + sizeof(int) * (size_t)nb));
+    CU(c, cudaMemsetAsync(c->ctl, 0, sizeof(kbp::SvdCtl) + sizeof(int) * (size_t)nb, c->stream));
+    CU(c, cudaMallocHost(&c->ctl_host, sizeof(kbp::SvdCtl)));
+    memset(c->ctl_host, 0, sizeof(kbp::SvdCtl));
     c->chain_elems = chain_elems; c->nb = nb; c->n_slots = n_slots;
   }
   CU(c, cudaMemsetAsync(c->slots, 0, sizeof(double) * (size_t)nb * n_slots, c->stream));
-  c->warm.clear();      // a new program layout: no warm-start buffer holds a basis any more
-  c->sched.clear();
   return KBP_OK;
 }
 
@@ -224,14 +250,32 @@ int64_t kbp_qr_work_elems(int64_t m, int64_t n) {
   int64_t k = m < n ? m : n;
   return m * n + m * k + k + 8;
 }
-int64_t kbp_svd_warm_elems(int64_t m, int64_t n, int64_t keep) { return kbp::svd_warm_elems(m, n, keep); }
+int64_t kbp_svd_warm_elems(int64_t, int64_t, int64_t) { return 0; }
 int64_t kbp_launch_count(const kbp_ctx* c) { return c ? c->launches : 0; }
-int64_t kbp_svd_sweeps(const kbp_ctx* c) { return c ? c->svd_sweeps : 0; }
-int kbp_svd_counters(const kbp_ctx* c, int64_t* out8) {
+int kbp_svd_counters(kbp_ctx* c, int64_t* out8) {
   if (!c || !out8) return KBP_E_ARG;
+  cudaSetDevice(c->device);
+  fold_device_counters(c);                 // synchronises the context's stream
   for (int i = 0; i < 8; ++i) out8[i] = c->counters[i];
-  out8[6] = c->graph_replays;
   return KBP_OK;
+}
+
+int kbp_graph_counters(const kbp_ctx* c, int64_t* out4) {
+  if (!c || !out4) return KBP_E_ARG;
+  out4[0] = c->graph_replays;
+  out4[1] = c->graph_captures;
+  int64_t ok = 0, bad = 0;
+  for (auto& kv : c->graphs) { ok += kv.second.exec != nullptr; bad += kv.second.bad; }
+  out4[2] = ok;
+  out4[3] = bad;
+  return KBP_OK;
+}
+
+int64_t kbp_svd_sweeps(kbp_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  fold_device_counters(c);
+  return c->counters[5] + c->counters[6];
 }
 
 int kbp_timer_start(kbp_ctx* c) {
@@ -279,57 +323,47 @@ static inline double bits_to_double(int64_t b) {
   return d;
 }
 
-// op lengths (words after the opcode) for the pre-scan; -1: variable (permute)
-static bool program_is_sync_free(const int64_t* w, int64_t n_words, int64_t* n_ops) {
-  int64_t i = 0;
-  *n_ops = 0;
-  while (i < n_words) {
-    const int64_t op = w[i];
-    ++*n_ops;
-    switch (op) {
-      case KBP_OP_PERMUTE: {
-        if (i + 4 >= n_words) return false;
-        const int64_t nd = w[i + 4];
-        if (nd < 1 || nd > 8) return false;
-        i += 5 + 2 * nd;
-        break;
-      }
-      case KBP_OP_GEMM: i += 9; break;
-      case KBP_OP_QR: i += 7; break;
-      case KBP_OP_SVD:
-        if (i + 11 >= n_words) return false;
-        if (!kbp::svd_small_fits(w[i + 5], w[i + 6])) return false;      // other SVD paths read flags back on the host
-        i += 12;
-        break;
-      case KBP_OP_NORMALIZE: i += 4; break;
-      case KBP_OP_EMBED: i += 12; break;
-      case KBP_OP_ZERO: i += 3; break;
-      case KBP_OP_SCALAR_TO_SLOT: i += 4; break;
-      case KBP_OP_NONFINITE: i += 4; break;
-      case KBP_OP_EYE: i += 4; break;
-      default: return false;
-    }
-  }
-  return i == n_words;
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph);
+
+static uint64_t program_hash(const int64_t* w, int64_t n_words) {
+  uint64_t h = 1469598103934665603ull;
+  for (int64_t i = 0; i < n_words; ++i) { h ^= (uint64_t)w[i]; h *= 1099511628211ull; }
+  return h ^ ((uint64_t)n_words * 0x9E3779B97F4A7C15ull);
 }
 
-static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words);
+static const size_t KBP_GRAPH_MAX = 256;
 
+int kbp_graph_policy(kbp_ctx* c, int64_t min_words, int capture_first) {
+  if (!c || min_words < 0) return KBP_E_ARG;
+  c->graph_min_words = min_words;
+  c->graph_first = capture_first != 0;
+  return KBP_OK;
+}
+
+// 1: the next kbp_run of this program is a single graph launch (asynchronous, no host decisions);  0: it will be run
+// op by op with host-driven loops (first sight of the program, graphs disabled, profiling)
+int kbp_graph_ready(kbp_ctx* c, const int64_t* w, int64_t n_words) {
+  if (!c || !w || !kbp::graphs_enabled() || c->profile || n_words < c->graph_min_words) return 0;
+  auto it = c->graphs.find(program_hash(w, n_words));
+  if (it == c->graphs.end()) return c->graph_first && c->graphs.size() < KBP_GRAPH_MAX;
+  return !it->second.bad && (it->second.exec != nullptr || it->second.seen >= 1 || c->graph_first);
+}
+
+// Every program is a CUDA graph from its second run on: the op stream is a constant launch sequence except for the
+// truncated SVDs, whose data-dependent loops are captured as conditional WHILE / IF nodes driven by one-thread decision
+// kernels (k_tsvd.cu, k_svd.cu).  The first run is host-driven (plain launches, control block read back per decision): it
+// validates the program and serves profilers, which want plain launches.
 int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
   static const bool graphs_on = kbp::graphs_enabled();
   static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
-  int64_t n_ops = 0;
-  if (!graphs_on || c->profile || sync_every || n_words < 256 || !program_is_sync_free(w, n_words, &n_ops) || n_ops < 32)
-    return run_ops(c, w, n_words);
-  // A program whose truncations all take the in-shared-memory Jacobi kernel never looks at the device from the host: its
-  // launch sequence is a constant.  Second run: capture it; afterwards: one graph launch instead of hundreds of launches.
-  uint64_t h = 1469598103934665603ull;
-  for (int64_t i = 0; i < n_words; ++i) { h ^= (uint64_t)w[i]; h *= 1099511628211ull; }
-  h ^= (uint64_t)n_words * 0x9E3779B97F4A7C15ull;
+  static const bool env_first = getenv("KBP_GRAPH_FIRST") != nullptr && atoi(getenv("KBP_GRAPH_FIRST")) != 0;
+  const bool capture_first = env_first || c->graph_first;
+  if (!graphs_on || c->profile || sync_every || n_words < c->graph_min_words) return run_ops(c, w, n_words, false, nullptr);
+  const uint64_t h = program_hash(w, n_words);
   auto it = c->graphs.find(h);
   if (it == c->graphs.end()) {
-    if (c->graphs.size() >= 64) return run_ops(c, w, n_words);
+    if (c->graphs.size() >= KBP_GRAPH_MAX) return run_ops(c, w, n_words, false, nullptr);
     it = c->graphs.emplace(h, kbp_ctx::GraphEntry()).first;
   }
   kbp_ctx::GraphEntry& ge = it->second;
@@ -337,48 +371,66 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   if (ge.exec) {
     CU(c, cudaGraphLaunch(ge.exec, c->stream));
     c->launches += ge.launches;
-    for (int k = 0; k < 8; ++k) c->counters[k] += ge.dcount[k];
+    for (int k = 0; k < 2; ++k) c->counters[k] += ge.dcount[k];
     ++c->graph_replays;
     return KBP_OK;
   }
-  if (ge.bad || ge.seen++ == 0) return run_ops(c, w, n_words);      // first run: plain (sets function attributes, warms up)
+  if (ge.bad || (ge.seen++ == 0 && !capture_first)) return run_ops(c, w, n_words, false, nullptr);
   const int64_t l0 = c->launches;
   int64_t c0[8];
   for (int k = 0; k < 8; ++k) c0[k] = c->counters[k];
-  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { ge.bad = true; cudaGetLastError(); return run_ops(c, w, n_words); }
-  const int rc = run_ops(c, w, n_words);
-  cudaGraph_t graph = nullptr;
-  const cudaError_t e1 = cudaStreamEndCapture(c->stream, &graph);
-  if (rc != KBP_OK || e1 != cudaSuccess || !graph) {
+  auto give_up = [&](const char* why) {
     ge.bad = true;
-    if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
     c->launches = l0;
     for (int k = 0; k < 8; ++k) c->counters[k] = c0[k];
-    return run_ops(c, w, n_words);
+    fprintf(stderr, "[kbp] graph capture of a %lld-word program failed (%s): running it with host-driven loops\n", (long long)n_words, why);
+    return run_ops(c, w, n_words, false, nullptr);
+  };
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return give_up("begin capture");
+  cudaStreamCaptureStatus st;
+  unsigned long long id;
+  cudaGraph_t top = nullptr;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  int rc = KBP_E_CUDA;
+  if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &top, &deps, &nd) == cudaSuccess && top) rc = run_ops(c, w, n_words, true, top);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e1 = cudaStreamEndCapture(c->stream, &graph);
+  if (rc != KBP_OK || e1 != cudaSuccess || !graph) {
+    for (int k = 0; k < 2; ++k) {                      // a body capture left open by a failure inside an op
+      cudaStreamCaptureStatus bs;
+      if (cudaStreamIsCapturing(c->body_stream[k], &bs) == cudaSuccess && bs != cudaStreamCaptureStatusNone) { cudaGraph_t g2 = nullptr; cudaStreamEndCapture(c->body_stream[k], &g2); }
+    }
+    if (graph) cudaGraphDestroy(graph);
+    return give_up(rc != KBP_OK ? c->err.c_str() : cudaGetErrorString(e1));
   }
   const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (e2 != cudaSuccess) { ge.bad = true; ge.exec = nullptr; cudaGetLastError(); c->launches = l0; for (int k = 0; k < 8; ++k) c->counters[k] = c0[k]; return run_ops(c, w, n_words); }
+  if (e2 != cudaSuccess) { ge.exec = nullptr; return give_up(cudaGetErrorString(e2)); }
   ge.launches = c->launches - l0;
   for (int k = 0; k < 8; ++k) ge.dcount[k] = c->counters[k] - c0[k];
+  ++c->graph_captures;
   CU(c, cudaGraphLaunch(ge.exec, c->stream));
   ++c->graph_replays;
   return KBP_OK;
 }
 
-static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph) {
   if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
-  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.warm = &c->warm; a.sched = &c->sched; a.tsvd_graphs = &c->tsvd_graphs; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
   a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
+  a.ctl = c->ctl; a.ctl_host = c->ctl_host; a.chain_state = reinterpret_cast<int*>(c->ctl + 1);
+  a.mask = nullptr; a.mask_want = 0;
+  a.capture = capture; a.top_graph = top_graph; a.body_stream[0] = c->body_stream[0]; a.body_stream[1] = c->body_stream[1]; a.depth = 0;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };
   auto slot_ok = [&](int64_t s) { return s >= -1 && s < c->n_slots; };
   int64_t i = 0;
-  int status = KBP_OK;
+  const int status = KBP_OK;
   static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
   while (i < n_words) {
     const int64_t op = w[i];
@@ -387,7 +439,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
 #define NEED(k) if (i + 1 + (k) > n_words) return fail(c, KBP_E_PROGRAM, std::string("truncated program") + where)
 #define BAD(msg) return fail(c, KBP_E_PROGRAM, std::string(msg) + where)
     cudaEvent_t pa = nullptr, pb = nullptr;
-    if (c->profile) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, c->stream); }
+    if (c->profile && !capture) { cudaEventCreate(&pa); cudaEventCreate(&pb); cudaEventRecord(pa, c->stream); }
     switch (op) {
       case KBP_OP_PERMUTE: {
         NEED(4);
@@ -435,12 +487,9 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
         if (m <= 0 || n <= 0 || keep <= 0 || keep > (m < n ? m : n) || !slot_ok(s0) || !slot_ok(s1)) BAD("svd: bad argument");
         if (!in_arena(A, m * n) || !in_arena(US, m * keep) || !in_arena(Vh, keep * n) || !in_arena(wk, kbp::svd_work_elems(m, n)))
           BAD("svd: buffer out of arena");
-        if (warm >= 0 && !in_arena(warm, kbp::svd_warm_elems(m, n, keep))) BAD("svd: warm-start buffer out of arena");
-        int sw = kbp::svd_truncate(a, A, US, Vh, wk, m, n, keep, (int)nrb, (int)s0, (int)s1, warm);
-        if (sw == -1) return fail(c, KBP_E_CUDA, std::string("svd: ") + cudaGetErrorString(cudaGetLastError()) + where);
-        if (sw == -2) { status = KBP_E_NONFINITE; c->err = std::string("svd: non-finite input") + where; }
-        else if (sw == -3) { if (status == KBP_OK) { status = KBP_E_SVD_NOCONV; c->err = std::string("svd: Jacobi did not converge") + where; } }
-        else c->svd_sweeps += sw;
+        (void)warm;                                    // reserved word of the op (no persistent basis any more)
+        const int sw = kbp::svd_truncate(a, A, US, Vh, wk, m, n, keep, (int)nrb, (int)s0, (int)s1);
+        if (sw < 0) return fail(c, KBP_E_CUDA, std::string("svd: ") + cudaGetErrorString(cudaGetLastError()) + where);
         i += 12;
         break;
       }
@@ -494,8 +543,8 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words) {
       default:
         BAD("unknown opcode");
     }
-    if (c->profile) { cudaEventRecord(pb, c->stream); c->spans.push_back({(int)op, pa, pb}); }
-    if (sync_every) {
+    if (c->profile && !capture) { cudaEventRecord(pb, c->stream); c->spans.push_back({(int)op, pa, pb}); }
+    if (sync_every && !capture) {
       cudaError_t e_ = cudaStreamSynchronize(c->stream);
       if (e_ == cudaSuccess) e_ = cudaGetLastError();
       if (e_ != cudaSuccess) return fail(c, KBP_E_CUDA, std::string("fault detected right after") + where + ": " + cudaGetErrorString(e_));

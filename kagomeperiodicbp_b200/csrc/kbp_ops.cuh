@@ -11,14 +11,22 @@
 
 namespace kbp {
 
-// captured first round (random start, fixed number of iterations, Rayleigh-Ritz, flag copy) of one subspace-iteration SVD op
-struct TsvdGraph {
-  cudaGraphExec_t exec = nullptr;
-  long long Qb = 0, f0 = 0, f1 = 0, f2 = 0;
-  int done = 0, seen = 0;
-  long long launches = 0;
-  bool bad = false, cold_fast = false;
+// Device-side control block of the truncation in flight on a context's stream.  Every data-dependent decision of a truncated
+// SVD (accept the subspace found / iterate further / hand the matrix to the exact Jacobi path; another Jacobi sweep or not) is
+// taken ON THE DEVICE by a one-thread kernel that writes this block and, when the program runs as a CUDA graph, sets the
+// condition of the WHILE / IF node that holds the optional work.  The host-driven mode (first run of a program, profilers)
+// reads the same block back instead.  Followed in memory by `int state[nb]`.
+struct SvdCtl {
+  int round;               // subspace rounds (Rayleigh-Ritz + check) done by the op in flight
+  int any_run;             // some chain wants another round
+  int any_exact;           // some chain needs the exact path
+  int sweeps;              // block-Jacobi sweeps done
+  int any_sweep;           // some chain has not converged yet
+  int pad[3];
+  long long counters[8];   // [2] truncations accepted from subspace iteration, [3] handed to the exact path, [4] exact-path runs,
+                           // [5] subspace iterations, [6] block-Jacobi sweeps, [7] truncations that did not converge
 };
+enum { CHAIN_RUNNING = 0, CHAIN_ACCEPTED = 1, CHAIN_EXACT = 2 };
 
 struct Arena {
   double2* base;          // nb * chain_stride complex128 elements
@@ -33,9 +41,19 @@ struct Arena {
   int* counters_dev;      // split-K tile semaphores: [nb][4096] ints, zero between launches
   int64_t* launches;      // host counter of kernel launches
   int64_t* counters;      // host counters [8]: see svd_truncate
-  std::unordered_map<long long, int>* sched;  // per-truncation iteration schedule learned from the previous run of the same program
-  std::unordered_map<unsigned long long, TsvdGraph>* tsvd_graphs;   // per-op CUDA graphs of the first round (cleared with the arena)
-  std::unordered_map<long long, int>* warm;   // warm-start buffers that hold a valid Ritz basis: offset -> block size
+  SvdCtl* ctl;            // device control block (+ state[nb]) of the truncation in flight, and its pinned host mirror
+  SvdCtl* ctl_host;
+  int* chain_state;       // device: [nb] CHAIN_* of the truncation in flight
+  // per-chain predicate of the launches issued through this Arena: a kernel works on chain c iff mask == nullptr or
+  // mask[c] == mask_want (chains of an ensemble converge after different numbers of rounds)
+  const int* mask;
+  int mask_want;
+  // whole-program stream capture in progress: data-dependent loops become conditional graph nodes whose bodies are captured
+  // on body_stream[depth]; conditional handles are created on top_graph
+  bool capture;
+  cudaGraph_t top_graph;
+  cudaStream_t body_stream[2];
+  int depth;
   // scratch for the Jacobi SVD convergence flags (device, nb doubles x 2) and its pinned host mirror
   double* svd_off;        // device: [6 + 32*160][nb]  (Jacobi: off current / previous sweep, ||A||_F^2; subspace: pivot, residual,
                           // ratio, discarded fraction, norms, partial sums of the check kernels)
@@ -51,13 +69,13 @@ inline cudaError_t stream_wait(const Arena& a) {
   return cudaEventSynchronize(a.block_event);
 }
 
-// CUDA graphs (whole sync-free programs in kbp_run, the first round of each subspace-iteration SVD): on by default,
+// CUDA graphs (whole programs in kbp_run, data-dependent loops as conditional nodes): on by default,
 // KBP_GRAPHS=0/1 decides explicitly.  Under Nsight Compute they are off unless asked for: on this toolchain the tool aborts
 // on stream capture from several threads with cluster launches, and a kernel-by-kernel profile wants plain launches anyway.
 inline bool graphs_enabled() {
   static const bool on = [] {
     if (const char* e = getenv("KBP_GRAPHS")) return atoi(e) != 0;
-    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) return false;
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("KBP_TSVD_PROF")) return false;
     return true;
   }();
   return on;
@@ -77,8 +95,14 @@ bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int6
 // slot_lognorm += ln ||A||_F (if nr_bulk); slot_trunc += sqrt(sum_discarded s^2 / sum s^2).
 // work: see svd_work_elems().  Returns the number of Jacobi sweeps used (max over chains), <0 on failure.
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
-                 int nr_bulk, int slot_lognorm, int slot_trunc, int64_t warm);
-int64_t svd_warm_elems(int64_t m, int64_t n, int64_t keep);
+                 int nr_bulk, int slot_lognorm, int slot_trunc);
+// opt-in of every kernel to > 48 KB of dynamic shared memory on the CURRENT device (called once per device by kbp_create)
+void init_device_attributes();
+// conditional node (WHILE or IF) appended to the capture in progress on a.stream; the returned Arena launches into its body.
+// end_body() closes the body capture.  Both return false on a CUDA error.
+bool begin_cond_body(const Arena& a, cudaGraphConditionalHandle h, bool is_while, Arena* body);
+bool end_body(const Arena& body);
+cudaGraphConditionalHandle new_cond_handle(const Arena& a);
 bool svd_small_fits(int64_t m, int64_t n);
 // ksplit >= 1: C partial sums side by side (C + s*m*n, s < ksplit), each over a contiguous range of k;  ksplit == 0: automatic
 // fused split (partials in the scratch area, last CTA per tile reduces) -- what gemm() does

@@ -20,7 +20,7 @@ EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
     "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
-    "kbp_profile_enable", "kbp_profile_read",
+    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy",
 ]
 
 
@@ -31,6 +31,13 @@ class EngineUnavailable(RuntimeError):
 class BubbleConError(RuntimeError):
     """raised where the reference prints and calls exit(1) (src/libs/bubblecon.py:2921-2949,
     src/libs/bmpslib.py:711-717); name follows src/_error_types.py."""
+
+
+def raise_if_not_converged(rc: int, where: str = ""):
+    """A truncation built from a factorisation that did not converge must not flow on silently (the reference retries a
+    failed SVD with a perturbed matrix and exits if that fails too, src/libs/bmpslib.py:741-745)."""
+    if rc == E_SVD_NOCONV:
+        raise BubbleConError(f"truncated SVD did not converge on the device{': ' + where if where else ''}")
 
 
 _lib = None
@@ -59,6 +66,9 @@ def load_library():
         lib.kbp_slots_read.argtypes = [P, P]; lib.kbp_slots_read.restype = I
         lib.kbp_slots_zero.argtypes = [P]; lib.kbp_slots_zero.restype = I
         lib.kbp_run.argtypes = [P, P, L]; lib.kbp_run.restype = I
+        lib.kbp_graph_ready.argtypes = [P, P, L]; lib.kbp_graph_ready.restype = I
+        lib.kbp_graph_counters.argtypes = [P, P]; lib.kbp_graph_counters.restype = I
+        lib.kbp_graph_policy.argtypes = [P, L, I]; lib.kbp_graph_policy.restype = I
         lib.kbp_sync.argtypes = [P]; lib.kbp_sync.restype = I
         lib.kbp_svd_work_elems.argtypes = [L, L]; lib.kbp_svd_work_elems.restype = L
         lib.kbp_qr_work_elems.argtypes = [L, L]; lib.kbp_qr_work_elems.restype = L
@@ -85,16 +95,8 @@ def svd_work_elems(m: int, n: int) -> int:
 
 
 def svd_warm_elems(m: int, n: int, keep: int) -> int:
-    """size of the persistent Ritz-basis buffer of one truncation (0: the op never takes the subspace path).
-    Mirrors kbp_svd_warm_elems / tsvd_block in k_tsvd.cu."""
-    p = min(m, n)
-    q = n if m <= n else m + n
-    if p <= 128 and p * q * 16 + p * 12 + 16 + ((p + 1) // 2) * 32 + 64 <= 225 * 1024:
-        return 0                                  # in-shared-memory Jacobi
-    b = min(112, (keep * 25 // 10 + 7) // 8 * 8)
-    if b < keep + 8 or b * 100 > p * 80:
-        return 0
-    return n * 112
+    """reserved (mirrors kbp_svd_warm_elems): KBP_OP_SVD keeps no state between runs."""
+    return 0
 
 
 def qr_work_elems(m: int, n: int) -> int:
@@ -169,6 +171,19 @@ class Engine:
         w = np.ascontiguousarray(words, dtype=np.int64)
         return self._check(self.lib.kbp_run(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)), soft=soft_errors)
 
+    def graph_ready(self, words: np.ndarray) -> bool:
+        """True: the next ``run`` of this program is one asynchronous CUDA-graph launch (no host decisions)."""
+        w = np.ascontiguousarray(words, dtype=np.int64)
+        return bool(self.lib.kbp_graph_ready(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)))
+
+    def graph_policy(self, min_words: int = 256, capture_first: bool = False):
+        self._check(self.lib.kbp_graph_policy(self.h, int(min_words), 1 if capture_first else 0))
+
+    def graph_counters(self) -> dict:
+        out = np.zeros(4, dtype=np.int64)
+        self._check(self.lib.kbp_graph_counters(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return {"graph_replays": int(out[0]), "graph_captures": int(out[1]), "graphs_alive": int(out[2]), "graph_capture_failures": int(out[3])}
+
     def sync(self):
         self._check(self.lib.kbp_sync(self.h))
 
@@ -179,11 +194,15 @@ class Engine:
         return int(self.lib.kbp_svd_sweeps(self.h))
 
     def svd_counters(self) -> dict:
-        """how the truncations were executed so far: in-smem Jacobi / subspace iteration / its fallbacks / block-Jacobi."""
+        """how the truncations were executed so far (synchronises): in-smem Jacobi / Householder-reduced / subspace iteration /
+        its hand-overs to the exact path / block-Jacobi runs; the device-decided ones are counted by the decision kernels."""
         out = np.zeros(8, dtype=np.int64)
         self._check(self.lib.kbp_svd_counters(self.h, out.ctypes.data_as(ctypes.c_void_p)))
-        return {"small": int(out[1]), "subspace": int(out[2]), "subspace_fallback": int(out[3]), "block_jacobi": int(out[4]),
-                "subspace_iterations": int(out[5]), "graph_replays": int(out[6])}
+        d = {"small": int(out[1]), "reduced": int(out[0]), "subspace": int(out[2]), "subspace_fallback": int(out[3]),
+             "block_jacobi": int(out[4]), "subspace_iterations": int(out[5]), "block_jacobi_sweeps": int(out[6]),
+             "not_converged": int(out[7])}
+        d.update(self.graph_counters())
+        return d
 
     def profile_enable(self, on: bool):
         self._check(self.lib.kbp_profile_enable(self.h, 1 if on else 0))

@@ -55,6 +55,7 @@ def reduce_to_core(unit_cell: UnitCell, messages: dict, N: int, chi: int, device
     res = {}
     for f in futs:
         side, outs, slots, rc = f.result()
+        bp.raise_if_not_converged(rc, f"ToCore contraction towards {side}")
         if slots[0, bp.SLOT_NONFINITE] > 0:
             raise bp.BubbleConError(f"non-finite values in the ToCore contraction towards {side}")
         o = outs[0]

@@ -12,6 +12,7 @@ import math
 
 import numpy as np
 
+from .engine import E_SVD_NOCONV, BubbleConError, raise_if_not_converged
 from .program import Program, _prod
 from .runtime import Compiled, get_engine
 
@@ -19,7 +20,9 @@ _EIG_SHIFT = 1.5
 
 
 class DeviceBackend:
-    def __init__(self, engine_key="ite", device: int = 0):
+    def __init__(self, engine_key="ite-percall", device: int = 0):
+        # its own engine: Compiled.load re-reserves the arena and uploads at offset 0, which would overwrite tensors a
+        # ResidentBackend on the same engine still holds
         self.eng = get_engine(engine_key, device)
         self._cache: dict = {}
         self.calls = 0
@@ -34,7 +37,8 @@ class DeviceBackend:
             outs = build(p, [t for _, t in dts])
             comp = Compiled(p, dts, [(f"o{k}", t) for k, t in enumerate(outs)])
             self._cache[key] = comp
-        o, sl, rc = comp.run(self.eng, [{f"i{k}": a for k, a in enumerate(inputs)}], soft_errors=(-4,))
+        o, sl, rc = comp.run(self.eng, [{f"i{k}": a for k, a in enumerate(inputs)}], soft_errors=(E_SVD_NOCONV,))
+        raise_if_not_converged(rc, f"device op {key[0] if isinstance(key, tuple) else key}")
         self.calls += 1
         return [o[0][f"o{k}"] for k in range(len(comp.out_layout))], sl[0]
 
@@ -111,7 +115,7 @@ class DeviceBackend:
         k = min(m.shape)
 
         def build(p, t):
-            us, vh = p.svd_trunc(t[0], k, False, 0, 1, warm=False)
+            us, vh = p.svd_trunc(t[0], k, False, 0, 1)
             g = p.matmul(us, us, k, k, m.shape[0], 2, 0)            # US^H US: its diagonal holds s^2
             return [us, vh, g]
         (us, vh, g), _ = self._run(("svd", m.shape), build, [m])
@@ -187,12 +191,13 @@ class ResidentBackend:
         if self.p.words:
             if self.p.peak + 64 > self.arena_elems:
                 raise MemoryError(f"resident ITE arena too small ({self.arena_elems} elements): set KBP_ITE_ARENA_GB")
-            self.eng.run(np.array(self.p.words, dtype=np.int64), soft_errors=(-4,))
-            self.p.words = []
+            words, self.p.words = self.p.words, []      # a failing run must not leave its ops queued in front of the next call
+            self.eng.run(np.array(words, dtype=np.int64))
             self.calls += 1
 
     def put(self, a) -> RArr:
         a = np.ascontiguousarray(a, dtype=np.complex128)
+        self._flush()                                   # an upload must not overtake queued ops that still read a recycled buffer
         t = self.p.new(a.shape if a.ndim else (1,))
         if self.p.peak + 64 > self.arena_elems:
             raise MemoryError(f"resident ITE arena too small ({self.arena_elems} elements): set KBP_ITE_ARENA_GB")
@@ -286,10 +291,13 @@ class ResidentBackend:
     def _svd_raw(self, m):
         M = self._dt(m)
         k = min(M.shape)
-        us, vh = self.p.svd_trunc(M, k, False, 0, 1, warm=False)
+        us, vh = self.p.svd_trunc(M, k, False, 0, 1)
         g = self.p.matmul(us, us, k, k, M.shape[0], 2, 0)
         self._flush()
         s = np.sqrt(np.maximum(np.real(np.diag(self.to_host(RArr(self, g)))), 0.0))
+        if self.eng.slots()[0, -1] > 0:                 # engine status slot (include/kbp.h): the factorisation did not converge
+            self.eng.slots_zero()
+            raise BubbleConError(f"SVD of a {M.shape[0]} x {M.shape[1]} matrix did not converge on the device")
         return RArr(self, us), s, RArr(self, vh)
 
     def svd(self, m):

@@ -13,7 +13,7 @@ import struct
 import numpy as np
 
 from .engine import (OP_EMBED, OP_EYE, OP_GEMM, OP_NONFINITE, OP_NORMALIZE, OP_PERMUTE, OP_QR, OP_SCALAR_TO_SLOT, OP_SVD,
-                     OP_ZERO, qr_work_elems, svd_warm_elems, svd_work_elems)
+                     OP_ZERO, qr_work_elems, svd_work_elems)
 
 ALIGN = 8  # complex128 elements (128 B)
 
@@ -83,7 +83,6 @@ class Program:
         self.qr_shapes: list[tuple[int, int]] = []
         self.gemm_flops = 0.0
         self._frozen = None
-        self._warm: list = []
 
     # ---------------- allocation ----------------
     def _alloc_raw(self, n: int) -> int:
@@ -237,19 +236,12 @@ class Program:
         q, r = self.qr(xh)
         return self.transpose(r, (1, 0), conj=True), self.transpose(q, (1, 0), conj=True)
 
-    def svd_trunc(self, x: DT, keep: int, nr_bulk: bool, slot_lognorm: int, slot_trunc: int, warm: bool = True):
-        """rank-`keep` truncated SVD.  ``warm``: give the op a persistent n x b buffer in which the engine keeps the Ritz
-        basis it found, so that the next run of the same program (the next BP iteration: nearly the same matrix) starts
-        its subspace iteration from there instead of from a pseudo-random block."""
+    def svd_trunc(self, x: DT, keep: int, nr_bulk: bool, slot_lognorm: int, slot_trunc: int):
+        """rank-`keep` truncated SVD (the last op word is reserved)."""
         m, n = x.shape
         us, vh = self.new((m, keep)), self.new((keep, n))
         work = self.new((svd_work_elems(m, n),))
-        woff = -1
-        if warm and svd_warm_elems(m, n, keep):
-            wb = self.new((svd_warm_elems(m, n, keep),), pinned=True)
-            self._warm.append(wb)
-            woff = wb.off
-        self._emit(OP_SVD, x.off, us.off, vh.off, work.off, m, n, keep, 1 if nr_bulk else 0, slot_lognorm, slot_trunc, woff)
+        self._emit(OP_SVD, x.off, us.off, vh.off, work.off, m, n, keep, 1 if nr_bulk else 0, slot_lognorm, slot_trunc, -1)
         mm, nn = max(m, n), min(m, n)
         self.flops += 4.0 * (14.0 * mm * nn * nn + 8.0 * nn ** 3)
         self.svd_shapes.append((m, n, keep))

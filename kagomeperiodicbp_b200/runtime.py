@@ -59,12 +59,16 @@ class Compiled:
                 buf[c, off:off + a.size] = a.reshape(-1)
         return buf
 
-    def run(self, eng: Engine, batch: list, soft_errors=()):
-        """returns (list of {name: ndarray} per chain, slots[nb, n_slots], rc)."""
-        nb = len(batch)
-        self.load(eng, nb)
+    def launch(self, eng: Engine, batch: list, soft_errors=()):
+        """first half of ``run``: load, ONE host->device copy of the packed inputs, start the program.  Returns rc.  When the
+        engine holds this program as a CUDA graph (``eng.graph_ready(self.words)``) the call returns as soon as the graph
+        launch is queued: several engines can be started back to back from one host thread."""
+        self.load(eng, len(batch))
         eng.upload(0, self.pack_inputs(batch))
-        rc = eng.run(self.words, soft_errors=soft_errors)
+        return eng.run(self.words, soft_errors=soft_errors)
+
+    def collect(self, eng: Engine, nb: int, rc: int = 0):
+        """second half of ``run``: ONE device->host copy of the packed outputs + the slot table (waits for the program)."""
         raw = eng.download(self.out_block.off, self.out_elems)
         slots = eng.slots()
         if rc == 0 and slots.shape[1] and np.any(slots[:, -1] > 0):     # engine-reserved status slot (include/kbp.h)
@@ -77,6 +81,11 @@ class Compiled:
                 d[name] = raw[c, q:q + n].reshape(shape).copy()
             outs.append(d)
         return outs, slots, rc
+
+    def run(self, eng: Engine, batch: list, soft_errors=()):
+        """returns (list of {name: ndarray} per chain, slots[nb, n_slots], rc)."""
+        rc = self.launch(eng, batch, soft_errors=soft_errors)
+        return self.collect(eng, len(batch), rc)
 
     # device-resident variant used by the benchmark: inputs already uploaded, outputs left on the device
     def run_resident(self, eng: Engine, soft_errors=()):

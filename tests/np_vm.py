@@ -63,6 +63,9 @@ class NumpyEngine:
     def slots_zero(self):
         self._slots[:] = 0
 
+    def graph_ready(self, words):
+        return True                      # the interpreter never blocks: exercises the one-thread launch / collect path
+
     def sync(self):
         pass
 

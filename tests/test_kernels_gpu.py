@@ -161,7 +161,8 @@ def test_svd_subspace_path(eng, m, n, keep, decay):
     res, sl = run(eng, lambda p, t: list(p.svd_trunc(t[0], keep, True, 0, 1)), batch)
     after = eng.svd_counters()
     if decay >= 0.05:
-        assert after["subspace"] == before["subspace"] + 1 and after["subspace_fallback"] == before["subspace_fallback"], (before, after)
+        # counted per chain by the device-side decision kernel
+        assert after["subspace"] == before["subspace"] + len(batch) and after["subspace_fallback"] == before["subspace_fallback"], (before, after)
     for c, ((a,), (us, vh)) in enumerate(zip(batch, res)):
         u, s, v = np.linalg.svd(a, full_matrices=False)
         fro = np.linalg.norm(s)

@@ -438,7 +438,7 @@ def main():
     ms_sharded, gather_bytes = None, 0
     if a.shard == "sides" and world > 1:
         from kagomeperiodicbp_b200 import parallel
-        sh = parallel.ShardedSides(N, cells[0], msgs_list[0], cfg, rank, world, dev)
+        sh = parallel.ShardedSides(N, cells[0], msgs_list[0], cfg, rank, world, dev, engine_key="sharded")
         for _ in range(a.warmup + 2):
             sh.step()
         tot = 0.0

@@ -84,6 +84,14 @@ int kbp_graph_ready(kbp_ctx* ctx, const int64_t* words, int64_t n_words);
 int kbp_graph_policy(kbp_ctx* ctx, int64_t min_words, int capture_first);
 int kbp_sync(kbp_ctx* ctx);
 
+/* device addresses of the arena ([nb][chain_elems] complex128), of the slot table ([nb][n_slots] doubles) and the CUDA stream
+ * handle of the context, for zero-copy exchange of block messages between the arenas of different GPUs (NCCL all-gather in
+ * kagomeperiodicbp_b200/parallel.py).  Valid until the next kbp_reserve that grows the arena. */
+uint64_t kbp_arena_ptr(const kbp_ctx* ctx);
+uint64_t kbp_slots_ptr(const kbp_ctx* ctx);
+uint64_t kbp_stream_ptr(const kbp_ctx* ctx);
+int64_t kbp_chain_elems(const kbp_ctx* ctx);
+
 /* workspace sizes (complex128 elements) needed by KBP_OP_SVD / KBP_OP_QR */
 int64_t kbp_svd_work_elems(int64_t m, int64_t n);
 int64_t kbp_qr_work_elems(int64_t m, int64_t n);

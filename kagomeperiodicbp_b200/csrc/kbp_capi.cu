@@ -238,6 +238,12 @@ int kbp_slots_zero(kbp_ctx* c) {
   return KBP_OK;
 }
 
+/* device addresses for zero-copy interoperation with NCCL / torch (multi-GPU exchange of messages between arenas) */
+uint64_t kbp_arena_ptr(const kbp_ctx* c) { return c ? (uint64_t)(uintptr_t)c->arena : 0; }
+uint64_t kbp_slots_ptr(const kbp_ctx* c) { return c ? (uint64_t)(uintptr_t)c->slots : 0; }
+uint64_t kbp_stream_ptr(const kbp_ctx* c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+int64_t kbp_chain_elems(const kbp_ctx* c) { return c ? c->chain_elems : 0; }
+
 int kbp_sync(kbp_ctx* c) {
   if (!c) return KBP_E_ARG;
   CU(c, cudaSetDevice(c->device));

@@ -20,7 +20,7 @@ EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
     "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
-    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy",
+    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
 ]
 
 
@@ -69,6 +69,9 @@ def load_library():
         lib.kbp_graph_ready.argtypes = [P, P, L]; lib.kbp_graph_ready.restype = I
         lib.kbp_graph_counters.argtypes = [P, P]; lib.kbp_graph_counters.restype = I
         lib.kbp_graph_policy.argtypes = [P, L, I]; lib.kbp_graph_policy.restype = I
+        for nm in ("kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr"):
+            getattr(lib, nm).argtypes = [P]; getattr(lib, nm).restype = ctypes.c_uint64
+        lib.kbp_chain_elems.argtypes = [P]; lib.kbp_chain_elems.restype = L
         lib.kbp_sync.argtypes = [P]; lib.kbp_sync.restype = I
         lib.kbp_svd_work_elems.argtypes = [L, L]; lib.kbp_svd_work_elems.restype = L
         lib.kbp_qr_work_elems.argtypes = [L, L]; lib.kbp_qr_work_elems.restype = L
@@ -102,6 +105,17 @@ def svd_warm_elems(m: int, n: int, keep: int) -> int:
 def qr_work_elems(m: int, n: int) -> int:
     k = min(m, n)
     return m * n + m * k + k + 8
+
+
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _cuda_view(ptr: int, n: int, typestr: str, device: int):
+    import torch
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArray(ptr, n, typestr), device=torch.device("cuda", device))
 
 
 class Engine:
@@ -175,6 +189,18 @@ class Engine:
         """True: the next ``run`` of this program is one asynchronous CUDA-graph launch (no host decisions)."""
         w = np.ascontiguousarray(words, dtype=np.int64)
         return bool(self.lib.kbp_graph_ready(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)))
+
+    # ---- zero-copy views for the multi-GPU message exchange (torch is plumbing here: device memory + NCCL) ----
+    def arena_tensor(self):
+        """the arena as a flat torch complex128 CUDA tensor [nb * chain_elems] sharing the engine's memory."""
+        return _cuda_view(int(self.lib.kbp_arena_ptr(self.h)), self.nb * int(self.lib.kbp_chain_elems(self.h)), "<c16", self.device)
+
+    def slots_tensor(self):
+        return _cuda_view(int(self.lib.kbp_slots_ptr(self.h)), self.nb * self.n_slots, "<f8", self.device)
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(int(self.lib.kbp_stream_ptr(self.h)), device=torch.device("cuda", self.device))
 
     def graph_policy(self, min_words: int = 256, capture_first: bool = False):
         self._check(self.lib.kbp_graph_policy(self.h, int(min_words), 1 if capture_first else 0))

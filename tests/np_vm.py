@@ -63,6 +63,18 @@ class NumpyEngine:
     def slots_zero(self):
         self._slots[:] = 0
 
+    # zero-copy views, as Engine's (torch CPU tensors sharing the interpreter's memory)
+    def arena_tensor(self):
+        import torch
+        return torch.from_numpy(self.arena.reshape(-1))
+
+    def slots_tensor(self):
+        import torch
+        return torch.from_numpy(self._slots.reshape(-1))
+
+    def torch_stream(self):
+        return None
+
     def graph_ready(self, words):
         return True                      # the interpreter never blocks: exercises the one-thread launch / collect path
 

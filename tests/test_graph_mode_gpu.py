@@ -120,10 +120,12 @@ def test_graph_ensemble_chains_take_different_branches(engines):
     assert d["subspace"] == 6 and d["subspace_fallback"] == 2 and d["block_jacobi"] == 2, d
     for c in (0, 1, 3):
         check(mats[c], oh[c]["o0"], oh[c]["o1"], sh[c], keep)
-    # each chain alone gives the same bits as inside the ensemble (chains do not influence each other)
+    # each chain alone gives the same truncated state as inside the ensemble (chains do not influence each other; the GEMM
+    # tiling depends on the number of chains, so only to rounding)
     for c in range(4):
         o1, s1, _ = comp.run(host, [batch[c]])
-        assert np.array_equal(o1[0]["o0"], oh[c]["o0"]) and np.array_equal(o1[0]["o1"], oh[c]["o1"]), c
+        assert np.linalg.norm(o1[0]["o0"] @ o1[0]["o1"] - oh[c]["o0"] @ oh[c]["o1"]) <= 1e-9, c
+        assert np.allclose(s1[0], sh[c], atol=1e-10)
 
 
 def test_whole_side_program_as_graph():

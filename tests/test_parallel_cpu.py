@@ -38,6 +38,15 @@ def _worker(rank, world, port, q):
         out_r, ref_msgs, err_r, _ = bp.bp_step_batch(N, [cell], [ref_msgs], cfg)[0]
         ref_errs.append(err_r)
     same = all(np.array_equal(a, b) for s in msgs for a, b in zip(msgs[s].mps.A, ref_msgs[s].mps.A))
+    # the persistent form: messages stay in the engines' arenas between iterations, one all-gather + one indexed copy per step
+    sh = parallel.ShardedSides(N, cell, msgs, cfg, rank, world, engine_key="sharded")
+    m2 = ref_msgs
+    for it in range(3):
+        e_sh, _, ok = sh.step()
+        _, m2, e_ref, _ = bp.bp_step_batch(N, [cell], [m2], cfg)[0]
+        same = same and ok and e_sh == e_ref
+    _, nxt = sh.messages()
+    same = same and all(np.array_equal(a, b) for s in nxt for a, b in zip(nxt[s].mps.A, m2[s].mps.A))
     gathered = parallel.gather_scalars([errs[-1], float(rank)], world)
     dist.destroy_process_group()
     q.put((rank, errs, ref_errs, same, nbytes, [g.tolist() for g in gathered]))

@@ -77,7 +77,7 @@ def make_geometry():
         print("geometry", N)
 
 
-def make_chain(D, N, check):
+def make_chain(D, N, check, sides=None):
     from algo.contract_tensor_network import contract_tensor_network
     from enums import ContractionDepth
     from lattices.directions import BlockSide
@@ -85,6 +85,8 @@ def make_chain(D, N, check):
     tn.connect_uniform_messages()
     out = {"A": uc.A, "B": uc.B, "C": uc.C, "chi": config.bp.trunc_dim}
     for side in BlockSide.all_in_counter_clockwise_order():
+        if sides is not None and str(side) not in sides:
+            continue
         mps, _, _ = contract_tensor_network(tn, side, ContractionDepth.ToMessage, config.bp.trunc_dim, allow_progressbar=False)
         for k, a in enumerate(mps.A):
             out[f"{side}_site{k}"] = a
@@ -159,6 +161,10 @@ if __name__ == "__main__":
         make_chain(2, 3, args.check)
         make_chain(3, 2, args.check)
         make_chain(3, 3, args.check)
+    if args.only == "d4":       # the benchmarked bond dimension (CPU-heavy: minutes); D=4, N=3 keeps two sides to bound the fixture size
+        make_chain(4, 2, args.check)
+        make_bp(4, 2, 0.1, args.check)
+        make_chain(4, 3, args.check, sides=("D", "UR"))
     if args.only in ("", "bp"):
         make_bp(2, 2, None, args.check)
         make_bp(2, 2, 0.1, args.check)

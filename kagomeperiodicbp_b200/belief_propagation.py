@@ -244,6 +244,23 @@ def compile_side_program(N: int, d: int, D: int, side: str, chi: int, msg_shapes
     return comp
 
 
+def contract_tensor_network(tn: "KagomeTNRepeatedUnitCell", direction: str, depth: str, bubblecon_trunc_dim: int, allow_progressbar: bool = False):
+    """(src/algo/contract_tensor_network.py:146-213)  one boundary-MPS contraction of the block with its messages attached:
+    -> (mps | (mantissa, exp10), contraction_order, MPSOrientation).  ``depth`` in {"ToMessage", "ToCore", "Full"}.  The truncation
+    algorithm follows the reference's rule (BubbleConGlobalConfig.bubblecon_compression: SVD up to D = 10, iterative above)."""
+    from .bubblecon import bubblecon
+    from .containers import BubbleConGlobalConfig
+    gc = BubbleConGlobalConfig()
+    cell = tn.unit_cell
+    msgs = {s: m.mps.A for s, m in tn.messages.items()}
+    T, E, A, K, P = block_tn.assemble(tn.N, cell.tensors(), msgs)
+    T, E, A = block_tn.connect_corner(tn.N, T, E, A, P, direction)
+    order = list(contraction_order.kagome_order(tn.N, direction, depth))
+    mps = bubblecon(T, E, A, SIDE_ANGLE[direction], order, D_trunc=bubblecon_trunc_dim, ket_tensors=K, separate_exp=gc.separate_exp,
+                    compression=gc.bubblecon_compression(tn.D))
+    return mps, order, MPSOrientation.standard(direction)
+
+
 def _is_arbitrary(cell) -> bool:
     return hasattr(cell, "site_tensors")
 
@@ -276,6 +293,10 @@ def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device
     for m in messages_list[1:]:
         assert _msg_shapes(m) == shapes, "batched cells must share message shapes"
     damping = config.damping if config.damping else None
+    from .containers import BubbleConGlobalConfig
+    if BubbleConGlobalConfig().bubblecon_compression(D)["type"] != "SVD":
+        raise NotImplementedError(f"block BP at D = {D} > 10: the reference switches bubblecon to iterative compression there; the fused "
+                                  "side programs truncate by SVD -- use contract_tensor_network(...) (stepwise device path) for such bonds")
     if config.fix_msg_each_step is False:
         raise NotImplementedError("BPConfig.fix_msg_each_step=False: the side programs always normalise the new message "
                                   "(the reference's default, src/algo/belief_propagation.py:158-159)")

@@ -6,6 +6,7 @@ defaults, so a reference user's configuration code carries over.
 from __future__ import annotations
 
 import copy
+import os
 from dataclasses import dataclass, field
 from typing import NamedTuple
 
@@ -27,6 +28,22 @@ class BlockSide:
     @staticmethod
     def opposite(side: str) -> str:
         return SIDE_OPPOSITE[side]
+
+
+@dataclass
+class BubbleConGlobalConfig:
+    """(src/containers/contractions.py:17-35) incl. the rule that selects the truncation algorithm of bubblecon from the bond
+    dimension: exact-SVD truncation up to D = 10, QR-only iterative compression (reduceDiter) above."""
+    override_progress_bar: bool | None = None
+    separate_exp: bool = True
+    iterative_compression_max_ier: int = 200
+    iterative_compression_error: float = 1e-8
+    d_threshold_for_compression: int = 10
+
+    def bubblecon_compression(self, D: int) -> dict:
+        if D <= self.d_threshold_for_compression:
+            return {"type": "SVD"}
+        return {"type": "iter", "max-iter": self.iterative_compression_max_ier, "err": self.iterative_compression_error}
 
 
 @dataclass
@@ -152,6 +169,38 @@ class UnitCell:
     A: np.ndarray
     B: np.ndarray
     C: np.ndarray
+    _file_name: str | None = None
+
+    # ---- persistence (src/unit_cell/definition.py:119-137): same call shapes; see persistence.py for the file format
+    def save(self, file_name: str | None = None, folder: str | None = None, asynchronous: bool = False) -> str:
+        from . import persistence
+        name = file_name or self._file_name or persistence.time_stamp()
+        fullpath = os.path.join(folder or persistence.DEFAULT_FOLDER, name + ".dat")
+        payload = persistence.unit_cell_payload(self, name)
+        if asynchronous:
+            persistence.saver().submit(payload, fullpath)
+            return fullpath
+        return persistence.write_payload(payload, fullpath)
+
+    @staticmethod
+    def load(file_name: str, folder: str | None = None, none_if_not_exist: bool = True):
+        from . import persistence
+        folder = folder or persistence.DEFAULT_FOLDER
+        try:
+            if file_name == "last":
+                files = sorted(os.listdir(folder), key=lambda f: os.path.getmtime(os.path.join(folder, f)))
+                file_name = files[-1]
+            if not file_name.endswith(".dat"):
+                file_name += ".dat"
+            a, b, c = persistence.read_unit_cell_arrays(os.path.join(folder, file_name))
+        except (FileNotFoundError, IndexError):
+            if none_if_not_exist:
+                return None
+            raise
+        return UnitCell(a, b, c, file_name[:-4])
+
+    def set_filename(self, name: str):
+        self._file_name = name
 
     def __getitem__(self, key):
         return {"A": self.A, "B": self.B, "C": self.C}[key]
@@ -163,7 +212,7 @@ class UnitCell:
         return (self.A, self.B, self.C)
 
     def copy(self) -> "UnitCell":
-        return UnitCell(self.A.copy(), self.B.copy(), self.C.copy())
+        return UnitCell(self.A.copy(), self.B.copy(), self.C.copy(), self._file_name)
 
     @staticmethod
     def random(d: int, D: int, seed=None) -> "UnitCell":

@@ -129,6 +129,61 @@ def measure_energies(unit_cell: UnitCell, messages: dict, N: int, chi: int, h=No
     return MeasurementsOnUnitCell(energies, rdms, expectations, ent)
 
 
+ENV_HERMICITY_THRESHOLD = 1e-4       # src/algo/imaginary_time_evolution/_constants.py
+DEBUG_MODE = False                   # the reference's configuration.json "debug_mode": violations raise instead of warning
+
+
+@dataclass
+class MatrixMetrics:
+    """(src/containers/density_matrices.py:5-13)"""
+    eigenvalues: list
+    negativity: float
+    sum_eigenvalues: complex
+    hermicity: float
+    norm: float
+    trace: complex
+    other: dict = field(default_factory=dict)
+
+
+def calc_metrics(rho: np.ndarray) -> MatrixMetrics:
+    """(src/algo/density_matrices.py:31-42) of a d^2 x d^2 density matrix: 4 x 4 host arithmetic, as in the reference."""
+    w = np.linalg.eigvals(rho)
+    return MatrixMetrics(eigenvalues=list(w), negativity=float(sum(abs(np.real(v)) for v in w if np.real(v) < 0)),
+                         sum_eigenvalues=complex(np.sum(w)), hermicity=float(np.linalg.norm(rho - np.conj(rho.T)) / np.linalg.norm(rho)),
+                         norm=float(np.linalg.norm(rho)), trace=complex(np.trace(rho)))
+
+
+def _raise_ite_error_or_print_warning(message: str):
+    if DEBUG_MODE:
+        raise ite.ITEError(message)
+    import warnings
+    warnings.warn(message, RuntimeWarning, stacklevel=3)
+
+
+def check_rdms_metrics(rdm) -> MatrixMetrics:
+    """the guard of every edge update (src/algo/imaginary_time_evolution/_tn_update.py:51-60): the two-site density matrix
+    must be Hermitian to 1e-4, of unit trace (sum of eigenvalues) to 1e-4, and positive up to a total negativity of 0.1."""
+    r = np.asarray(rdm)
+    d = r.shape[0]
+    m = calc_metrics(np.transpose(r, (0, 2, 1, 3)).reshape(d * d, d * d))          # rho_ij_to_rho (density_matrices.py:11-18)
+    if m.hermicity > ENV_HERMICITY_THRESHOLD:
+        _raise_ite_error_or_print_warning(f"env_hermicity={m.hermicity}")
+    if abs(np.real(m.sum_eigenvalues) - 1) > ENV_HERMICITY_THRESHOLD:
+        _raise_ite_error_or_print_warning(f"env is not psd. sum-eigenvalues={np.real(m.sum_eigenvalues)}")
+    if m.negativity > 0.1:
+        _raise_ite_error_or_print_warning(f"env is not psd. negativity={m.negativity}")
+    return m
+
+
+def _original_negativity_ratio(eigen_vals) -> float:
+    """(_tn_update.py:63-73)"""
+    if eigen_vals is None:
+        return 0.0
+    ev = np.real(np.asarray(eigen_vals))
+    pos, neg = float(np.sum(ev[ev > 0])), float(abs(np.sum(ev[ev < 0])))
+    return neg / pos if pos > 0 else 0.0
+
+
 @dataclass
 class ITEStepStats:
     bp_iterations: int = 0
@@ -138,11 +193,15 @@ class ITEStepStats:
     t_bp: float = 0.0
     t_reduce: float = 0.0
     t_update: float = 0.0
+    env_metrics: MatrixMetrics | None = None      # of the RDM after the update (what ite_update_unit_cell returns, :183-205)
+    saved_to: str | None = None
 
 
 def ite_edge_update(unit_cell: UnitCell, messages: dict | None, N: int, mode: str, edge: str, delta_t: float, bp_config: BPConfig,
-                    chi: int, h=None, normalize: bool = True):
-    """one loop body of ite_per_mode with bp_every_edge=True: -> (unit_cell, messages, energy_after, ITEStepStats)."""
+                    chi: int, h=None, normalize: bool = True, save: bool | str = False):
+    """one loop body of ite_per_mode with bp_every_edge=True: -> (unit_cell, messages, energy_after, ITEStepStats).
+    ``save``: keep a copy of the updated unit cell on disk as the reference does after every update (_tn_update.py:203);
+    True = default folder, a string = that folder.  The write happens on the background saver thread (persistence.py)."""
     st = ITEStepStats()
     h = ite.heisenberg_afm() if h is None else np.asarray(h)
     g = ite.g_from_exp_h(h, delta_t)
@@ -155,21 +214,26 @@ def ite_edge_update(unit_cell: UnitCell, messages: dict | None, N: int, mode: st
     env12 = reduce_to_core(unit_cell, messages, N, chi)
     ti, tj, env, info = edge_tn(unit_cell, env12, N, mode, edge, chi)
     t2 = time.perf_counter()
-    ite.rho_ij(B, ti, tj, env)                                           # _measures_on_edge before the update (_tn_update.py:181)
+    check_rdms_metrics(ite.rho_ij(B, ti, tj, env))                       # _measures_on_edge before the update (_tn_update.py:181)
     d_virtual = ti.shape[1]
-    ti_new, tj_new, _ = ite.apply_2local_gate(B, g, d_virtual, ti, tj, env)
+    ti_new, tj_new, origin_eigen_vals = ite.apply_2local_gate(B, g, d_virtual, ti, tj, env)
     last = getattr(ite.ALS_optimization, "last", None)
     if last:
         st.als_iterations, st.truncation_distance = last["iterations"], last["distance"]
     rho = ite.rho_ij(B, ti_new, tj_new, env)
     energy = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
+    st.env_metrics = check_rdms_metrics(rho)
+    st.env_metrics.other["original_negativity_ratio"] = _original_negativity_ratio(origin_eigen_vals)
     if normalize:
         ti_new = B.scale(ti_new, 1.0 / B.norm(ti_new))
         tj_new = B.scale(tj_new, 1.0 / B.norm(tj_new))
     new_cell = edge_env.write_back(unit_cell.tensors(), info, ti_new, tj_new)
     t3 = time.perf_counter()
     st.t_bp, st.t_reduce, st.t_update = t1 - t0, t2 - t1, t3 - t2
-    return UnitCell(*new_cell), messages, energy, st
+    out_cell = UnitCell(*new_cell, unit_cell._file_name if isinstance(unit_cell, UnitCell) else None)
+    if save:
+        st.saved_to = out_cell.save(folder=save if isinstance(save, str) else None, asynchronous=True)
+    return out_cell, messages, energy, st
 
 
 def ite_per_mode(unit_cell: UnitCell, messages: dict | None, N: int, mode: str, edge_order, bp_config: BPConfig, chi: int, h=None):

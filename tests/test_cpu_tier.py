@@ -45,12 +45,15 @@ def test_block_counts():
 
 
 # ------------------------------------------------------------------ oracle vs reference
-@pytest.mark.parametrize("D,N", [(2, 2), (2, 3), (3, 2)])
+@pytest.mark.parametrize("D,N", [(2, 2), (2, 3), (3, 2), (4, 2)])
 def test_oracle_chain_matches_reference(D, N):
+    """(D=4 is the benchmarked bond dimension: chain_D4_N2.npz, and chain_D4_N3.npz on the GPU tier)"""
     g = golden(f"chain_D{D}_N{N}.npz")
     cell = (g["A"], g["B"], g["C"])
     um = bp_np.uniform_messages(N, D)
     for side in SIDES:
+        if f"{side}_site0" not in g:
+            continue
         mine = bp_np.outgoing_message(N, cell, um, side, int(g["chi"]))
         assert dense_rel_diff(golden_mps(g, side), mine) < 1e-12
 
@@ -177,3 +180,54 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S), fn
+
+
+def test_compression_selection_rule_and_chain_entry(vm_engines):
+    """the reference's rule D <= 10 -> SVD, else iterative (src/containers/contractions.py:27-35), and the
+    contract_tensor_network mirror that applies it (ToMessage chain on the interpreter == oracle)."""
+    from kagomeperiodicbp_b200 import belief_propagation as bp
+    from kagomeperiodicbp_b200.containers import BubbleConGlobalConfig, UnitCell
+    gc = BubbleConGlobalConfig()
+    assert gc.bubblecon_compression(10) == {"type": "SVD"}
+    assert gc.bubblecon_compression(11) == {"type": "iter", "max-iter": 200, "err": 1e-8}
+    D, N = 2, 2
+    cell = UnitCell.random(2, D, seed=4)
+    tn = bp.KagomeTNRepeatedUnitCell(cell, N)
+    tn.connect_uniform_messages()
+    mps, order, orientation = bp.contract_tensor_network(tn, "UR", "ToMessage", 8)
+    mine = bp_np.outgoing_message(N, cell.tensors(), bp_np.uniform_messages(N, D), "UR", 8)
+    from helpers import to_oracle_mps
+    assert dense_rel_diff(mine, to_oracle_mps(mps)) < 1e-12
+    assert orientation.open_towards == "UR" and len(order) == 5 * (2 * N - 1) + 21
+
+
+def test_unit_cell_persistence_and_rdm_guard(tmp_path):
+    """per-step save of the unit cell (async writer, atomic replace) and the RDM guard of the ITE update
+    (src/algo/imaginary_time_evolution/_tn_update.py:51-60, 203)."""
+    import warnings
+    from kagomeperiodicbp_b200 import ite_flow, persistence
+    from kagomeperiodicbp_b200.containers import UnitCell
+    uc = UnitCell.random(2, 3, seed=1)
+    uc.set_filename("cell_a")
+    p = uc.save(folder=str(tmp_path), asynchronous=True)
+    persistence.saver().flush()
+    back = UnitCell.load("cell_a", folder=str(tmp_path))
+    assert p.endswith("cell_a.dat") and all(np.array_equal(a, b) for a, b in zip(back.tensors(), uc.tensors()))
+    assert UnitCell.load("last", folder=str(tmp_path))._file_name == "cell_a"
+    assert UnitCell.load("missing", folder=str(tmp_path)) is None
+    rho = np.zeros((2, 2, 2, 2), complex)
+    rho[0, 0, 0, 0] = rho[1, 1, 1, 1] = 0.5
+    m = ite_flow.check_rdms_metrics(rho)
+    assert m.hermicity == 0 and abs(m.sum_eigenvalues - 1) < 1e-15 and m.negativity == 0
+    bad = rho.copy()
+    bad[0, 1, 0, 0] = 0.3                                    # not Hermitian
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ite_flow.check_rdms_metrics(bad)
+    assert any("hermicity" in str(x.message) for x in w)
+    ite_flow.DEBUG_MODE = True
+    try:
+        with pytest.raises(ite_flow.ite.ITEError):
+            ite_flow.check_rdms_metrics(bad)
+    finally:
+        ite_flow.DEBUG_MODE = False

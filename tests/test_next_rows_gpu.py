@@ -1,8 +1,7 @@
-"""Device runs of the two SURVEY 8f rows that were wired after the round's GPU budget was spent: bubblecon with iterative
-(reduceDiter) compression and the non-repeated block (KagomeTNArbitrary).  Their op streams are validated on the CPU against
-the reference fixtures through the numpy interpreter (tests/test_chain_iter_cpu.py, tests/test_arbitrary_tn_cpu.py) and every
-kernel they launch is parity-tested on the B200 by the other files; these end-to-end device runs have NOT been executed yet,
-so they only run when asked for (KBP_RUN_UNVERIFIED=1) instead of gating the suite."""
+"""GPU tier: device runs of the SURVEY 8f rows -- bubblecon with iterative (reduceDiter) compression, the non-repeated block
+(KagomeTNArbitrary), the shift-averaged measurement, the best D=3 unit cell -- and the run-to-run determinism of a BP step.
+Their op streams are also validated on the CPU against the reference fixtures through the numpy interpreter
+(tests/test_chain_iter_cpu.py, tests/test_arbitrary_tn_cpu.py, tests/test_shifting_cpu.py)."""
 import os
 
 import numpy as np
@@ -10,8 +9,7 @@ import pytest
 
 from helpers import golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("KBP_RUN_UNVERIFIED") != "1", reason="not yet run on a GPU (set KBP_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("side", ["D", "UL"])

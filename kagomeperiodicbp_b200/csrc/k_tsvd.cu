@@ -18,6 +18,7 @@
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
 
+#include <cooperative_groups.h>
 #include <mutex>
 #include <vector>
 
@@ -127,53 +128,24 @@ __global__ void tsvd_randq_kernel(cplx* __restrict__ base, long long chain_strid
 // columns of pivot/diagonal.  Outputs: R (b x b, upper, row-major), Dinv (b entries, 1/R_jj in .x).
 constexpr int CNB = 16;
 
-__global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
-                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat, const int* __restrict__ mask,
-                                                    int mask_want) {
-  if (mask && mask[blockIdx.x] != mask_want) return;
-  extern __shared__ __align__(16) unsigned char ch_raw[];
-  const int ld = b + 1;                                            // odd row stride: the 16 rows of a panel fall into different banks
-  cplx* S = reinterpret_cast<cplx*>(ch_raw);                      // b x ld
-  double* diag0 = reinterpret_cast<double*>(S + (size_t)b * ld);   // original diagonal
-  double* dinv = diag0 + b;                                        // 1 / R_jj (0 for dropped columns)
-  double* piv = dinv + b;                                          // pivot of each column (-1: dropped)
-  __shared__ double sh_min;
-  __shared__ cplx rowbuf[4 * CNB];                                 // [parity][row line | column line]
-  cplx* cb = base + (long long)blockIdx.x * chain_stride;
-  const cplx* G = cb + G_;
-  const int t = threadIdx.x, nt = blockDim.x;
-#ifdef KBP_CHOL_TIMING
-  long long tk[6] = {0, 0, 0, 0, 0, 0};
-  long long tq = clock64();
-#define CHTICK(k) { const long long now_ = clock64(); tk[k] += now_ - tq; tq = now_; }
-#else
-#define CHTICK(k)
-#endif
-  {
-    // sum of the split-K partial Gram matrices; (row, column) from the warp / lane, no integer division, all partials of
-    // several rows in flight at once
-    const int lane = t & 31, w = t >> 5, nw = nt >> 5;
-    const long long bb = (long long)b * b;
-    for (int r = w; r < b; r += nw) {
-      for (int c = lane; c < b; c += 32) {
-        const cplx* gp = G + (long long)r * b + c;
-        cplx v = gp[0];
-        if (nsplit == 4) {
-          const cplx v1 = gp[bb], v2 = gp[2 * bb], v3 = gp[3 * bb];
-          v = cadd(cadd(v, v1), cadd(v2, v3));
-        } else {
-          for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, gp[(long long)sp * bb]);
-        }
-        S[r * ld + c] = v;
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = t; i < b; i += nt) diag0[i] = S[i * ld + i].x;
-  if (t == 0) sh_min = 1.0;
-  __syncthreads();
-  CHTICK(0)
+struct CholWork {
+  cplx* S;          // b x ld, upper triangle = Gram matrix in, Cholesky factor R out
+  double* diag0;    // [b] original diagonal
+  double* dinv;     // [b] 1 / R_jj (0 for dropped columns)
+  double* piv;      // [b] pivot of each column (-1: dropped)
+  cplx* rowbuf;     // [4 * CNB] pivot row / column lines, double buffered
+  int ld;
+};
 
+// Blocked Cholesky of the b x b Hermitian matrix in w.S (upper triangle read, R written in place), all threads of the CTA.
+// Called with w.diag0 filled and the block synchronised.
+__device__ __forceinline__ void chol_factor(const CholWork& w, int b, int t, int nt) {
+  cplx* S = w.S;
+  double* diag0 = w.diag0;
+  double* dinv = w.dinv;
+  double* piv = w.piv;
+  cplx* rowbuf = w.rowbuf;
+  const int ld = w.ld;
   for (int p0 = 0; p0 < b; p0 += CNB) {
     const int p1 = p0 + CNB < b ? p0 + CNB : b, pw = p1 - p0;
     // ---- phase A
@@ -210,7 +182,6 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
       if (in && col >= row) S[(p0 + row) * ld + p0 + col] = v;       // R (upper)
     }
     __syncthreads();
-    CHTICK(1)
     const int rem = b - p1;
     if (rem > 0) {
       // ---- phase B: R[r][l] = (S[r][l] - sum_{r' < r} conj(R[r'][r]) R[r'][l]) / R[r][r],  l >= p1
@@ -238,7 +209,6 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
         if (valid) S[(p0 + r) * ld + l] = acc;
       }
       __syncthreads();
-      CHTICK(2)
       // ---- phase C: trailing update  S[i][l] -= sum_{r in panel} conj(R[r][i]) R[r][l],  p1 <= i <= l
       // upper triangle only, folded into a (rem + 1) x ceil(rem / 2) rectangle: row rr carries matrix row rr (rem - rr entries)
       // followed by matrix row rem - 1 - rr (rr + 1 entries)
@@ -264,19 +234,18 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
         S[i * ld + l] = x;
       }
       __syncthreads();
-      CHTICK(3)
     }
   }
-  cplx* R = cb + R_;
-  for (int r = t >> 5; r < b; r += nt >> 5)
-    for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
-  cplx* Dv = cb + Dinv_;
-  for (int i = t; i < b; i += nt) Dv[i] = cmake(dinv[i], 0.0);
-  // inverses of the 16 x 16 diagonal blocks (what the blocked triangular solve multiplies by), all panels in parallel
-  cplx* Xd = cb + Xd_;
+}
+
+// inverses of the 16 x 16 diagonal blocks of R (what the blocked triangular solve multiplies by), all panels in parallel:
+// thread (panel, column l) does the back substitution up column l of X = R_pp^{-1}, a 16-step dependent chain.
+// Xd: nblk x 16 x 16 (shared or global memory).
+__device__ __forceinline__ void chol_diag_inverses(const CholWork& w, int b, cplx* __restrict__ Xd, int t, int nt) {
+  const cplx* S = w.S;
+  const double* dinv = w.dinv;
+  const int ld = w.ld;
   const int nblk = (b + CNB - 1) / CNB;
-  // thread (panel, column l): back substitution up column l of X = R_pp^{-1}, right-looking (x_il = -dinv_i sum_{r > i} R[i][r] x_rl):
-  // a 16-step dependent chain per thread, all panels and columns in parallel
   for (int e = t; e < nblk * CNB; e += nt) {
     const int pb = e / CNB, l = e - pb * CNB;
     const int p0 = pb * CNB, pw = (p0 + CNB < b ? CNB : b - p0);
@@ -303,18 +272,250 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
       for (int i = 0; i < CNB; ++i) Xp[i * CNB + l] = cmake(0.0, 0.0);
     }
   }
-  CHTICK(4)
-#ifdef KBP_CHOL_TIMING
-  if (t == 0 && blockIdx.x == 0) printf("[chol b=%d] load %lld  A %lld  B %lld  C %lld  tail %lld cycles\n", b, tk[0], tk[1], tk[2], tk[3], tk[4]);
-#endif
-  if (t < 32) {                                                    // smallest pivot / diagonal over the live columns
-    double mn = 1.0;
-    for (int i = t; i < b; i += 32)
-      if (piv[i] > 0.0) mn = fmin(mn, piv[i] / diag0[i]);
+}
+
+// smallest pivot / diagonal over the live columns (first warp; the value is valid in lane 0)
+__device__ __forceinline__ double chol_min_pivot(const CholWork& w, int b, int t) {
+  double mn = 1.0;
+  for (int i = t; i < b; i += 32)
+    if (w.piv[i] > 0.0) mn = fmin(mn, w.piv[i] / w.diag0[i]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  return mn;
+}
+
+__global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
+                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat, const int* __restrict__ mask,
+                                                    int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
+  extern __shared__ __align__(16) unsigned char ch_raw[];
+  __shared__ cplx rowbuf[4 * CNB];
+  CholWork w;
+  w.ld = b + 1;                                                    // odd row stride: the 16 rows of a panel fall into different banks
+  w.S = reinterpret_cast<cplx*>(ch_raw);
+  w.diag0 = reinterpret_cast<double*>(w.S + (size_t)b * w.ld);
+  w.dinv = w.diag0 + b;
+  w.piv = w.dinv + b;
+  w.rowbuf = rowbuf;
+  cplx* S = w.S;
+  const int ld = w.ld;
+  cplx* cb = base + (long long)blockIdx.x * chain_stride;
+  const cplx* G = cb + G_;
+  const int t = threadIdx.x, nt = blockDim.x;
+  {
+    // sum of the split-K partial Gram matrices; (row, column) from the warp / lane, no integer division, all partials of
+    // several rows in flight at once
+    const int lane = t & 31, wp = t >> 5, nw = nt >> 5;
+    const long long bb = (long long)b * b;
+    for (int r = wp; r < b; r += nw) {
+      for (int c = lane; c < b; c += 32) {
+        const cplx* gp = G + (long long)r * b + c;
+        cplx v = gp[0];
+        if (nsplit == 4) {
+          const cplx v1 = gp[bb], v2 = gp[2 * bb], v3 = gp[3 * bb];
+          v = cadd(cadd(v, v1), cadd(v2, v3));
+        } else {
+          for (int sp = 1; sp < nsplit; ++sp) v = cadd(v, gp[(long long)sp * bb]);
+        }
+        S[r * ld + c] = v;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
+  __syncthreads();
+  chol_factor(w, b, t, nt);
+  cplx* R = cb + R_;
+  for (int r = t >> 5; r < b; r += nt >> 5)
+    for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
+  cplx* Dv = cb + Dinv_;
+  for (int i = t; i < b; i += nt) Dv[i] = cmake(w.dinv[i], 0.0);
+  chol_diag_inverses(w, b, cb + Xd_, t, nt);
+  if (t < 32) {
+    const double mn = chol_min_pivot(w, b, t);
     if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], mn);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky-QR of a tall panel in ONE launch:  Out (rows x b) = Y R^{-1},  Y^H Y = R^H R.
+// A cluster of C CTAs splits the rows (RL = 32 or 64 each); every CTA
+//   1. loads its slab into shared memory and forms the partial Gram matrix of it (upper triangle),
+//   2. takes part in an all-reduce over distributed shared memory: CTA k sums slice k of all partials in rank order (every
+//      CTA ends up with bitwise the same matrix) and stores the sums into every CTA's copy,
+//   3. runs the Cholesky factorisation redundantly (same code as chol_kernel: the factorisation is latency bound, not
+//      work bound, and this way R never leaves the SM),
+//   4. solves its slab against R in place (blocked forward substitution with the inverses of the diagonal blocks).
+// Replaces split-K Gram GEMM + chol_kernel + trsm_kernel (three launches, R and the Gram partials through L2).
+// out_rows == 0: only R is wanted.  Rank 0 writes R and the pivot statistic.
+namespace cgx = cooperative_groups;
+
+struct CholQrArgs {
+  long long Y, Out, R;     // arena offsets; Out < 0: R only; R < 0: R not stored
+  int rows, b, rl;         // rl = rows per CTA
+  const int* mask;
+  int mask_want;
+};
+
+__global__ void __launch_bounds__(512) cholqr_cluster_kernel(cplx* __restrict__ base, long long chain_stride, CholQrArgs g, double* __restrict__ stat) {
+  if (g.mask && g.mask[blockIdx.y] != g.mask_want) return;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) unsigned char cq_raw[];
+  __shared__ cplx rowbuf[4 * CNB];
+  const int b = g.b, ld = b + 1, rl = g.rl, nblk = (b + CNB - 1) / CNB;
+  CholWork w;
+  w.ld = ld;
+  w.S = reinterpret_cast<cplx*>(cq_raw);                           // b x ld
+  cplx* Ys = w.S + (size_t)b * ld;                                 // rl x ld: the CTA's slab, solved in place
+  cplx* Xs = Ys + (size_t)rl * ld;                                 // nblk x 16 x 16
+  cplx* tmp = Xs + (size_t)nblk * CNB * CNB;                       // 32 x 17
+  w.diag0 = reinterpret_cast<double*>(tmp + 32 * 17);
+  w.dinv = w.diag0 + b;
+  w.piv = w.dinv + b;
+  w.rowbuf = rowbuf;
+  cplx* S = w.S;
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, wp = t >> 5, nw = nt >> 5;
+  const int r0 = rank * rl;
+  // ---- 1. slab
+  {
+    const cplx* Y = cb + g.Y;
+    for (int r = wp; r < rl; r += nw) {
+      const bool ok = r0 + r < g.rows;
+      for (int c = lane; c < b; c += 32) Ys[r * ld + c] = ok ? Y[(long long)(r0 + r) * b + c] : cmake(0.0, 0.0);
+    }
+  }
+  __syncthreads();
+  // partial Gram, upper triangle: thread -> 2 x 2 block (i, i + 1) x (j, j + 1) of the b x b matrix, rows of the slab streamed
+  {
+    const int hb = (b + 1) / 2;
+    for (int e = t; e < hb * hb; e += nt) {
+      const int bi = e / hb, bj = e - bi * hb;
+      if (bj < bi) continue;
+      const int i = 2 * bi, j = 2 * bj;
+      const bool i1 = i + 1 < b, j1 = j + 1 < b;
+      cplx a00 = cmake(0.0, 0.0), a01 = a00, a10 = a00, a11 = a00;
+      for (int r = 0; r < rl; ++r) {
+        const cplx yi = Ys[r * ld + i], yj = Ys[r * ld + j];
+        const cplx yi1 = i1 ? Ys[r * ld + i + 1] : cmake(0.0, 0.0), yj1 = j1 ? Ys[r * ld + j + 1] : cmake(0.0, 0.0);
+        a00 = cadd(a00, ccmul(yi, yj));
+        a01 = cadd(a01, ccmul(yi, yj1));
+        a10 = cadd(a10, ccmul(yi1, yj));
+        a11 = cadd(a11, ccmul(yi1, yj1));
+      }
+      S[i * ld + j] = a00;
+      if (j1) S[i * ld + j + 1] = a01;
+      if (i1) S[(i + 1) * ld + j] = a10;                           // (below the diagonal when bi == bj: never read)
+      if (i1 && j1) S[(i + 1) * ld + j + 1] = a11;
+    }
+  }
+  // ---- 2. all-reduce over the cluster (rank order: deterministic and identical everywhere)
+  if (C > 1) {
+    cluster.sync();
+    const int total = b * ld;
+    const int per = (total + C - 1) / C, e0 = rank * per, e1 = min(total, e0 + per);
+    cplx acc[4];                                                   // host guarantees per <= 4 * blockDim
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + t + k * nt;
+      const int r = e / ld, c = e - r * ld;
+      cplx v = cmake(0.0, 0.0);
+      if (e < e1 && c >= r && c < b) {                             // upper triangle only
+        for (int q = 0; q < C; ++q) v = cadd(v, cluster.map_shared_rank(S, q)[e]);
+      }
+      acc[k] = v;
+    }
+    cluster.sync();                                                // every partial has been read
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + t + k * nt;
+      const int r = e / ld, c = e - r * ld;
+      if (e < e1 && c >= r && c < b) {
+        for (int q = 0; q < C; ++q) cluster.map_shared_rank(S, q)[e] = acc[k];
+      }
+    }
+    cluster.sync();
+  } else {
+    __syncthreads();
+  }
+  for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
+  __syncthreads();
+  // ---- 3. Cholesky (redundant per CTA)
+  chol_factor(w, b, t, nt);
+  if (rank == 0) {
+    if (g.R >= 0) {
+      cplx* R = cb + g.R;
+      for (int r = wp; r < b; r += nw)
+        for (int c = lane; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
+    }
+    if (t < 32) {
+      const double mn = chol_min_pivot(w, b, t);
+      if (t == 0) stat[blockIdx.y] = fmin(stat[blockIdx.y], mn);
+    }
+  }
+  if (g.Out < 0) return;
+  chol_diag_inverses(w, b, Xs, t, nt);
+  __syncthreads();
+  // ---- 4. slab <- slab R^{-1}: 32 rows per pass, 16 threads per row (half warp), panel by panel
+  for (int pass = 0; pass < rl; pass += 32) {
+    const int r = pass + (t >> 4), c = t & 15;
+    cplx* xr = Ys + r * ld;
+    cplx* tr = tmp + (t >> 4) * 17;
+    for (int pb = 0; pb < nblk; ++pb) {
+      const int p0 = pb * CNB, col = p0 + c;
+      cplx acc = col < b ? xr[col] : cmake(0.0, 0.0);
+      {
+        cplx acc2 = cmake(0.0, 0.0);
+        int i = 0;
+        for (; i + 1 < p0; i += 2) {                                 // two independent chains; R[i][col] from the factor in S
+          const cplx v0 = cmul(xr[i], col < b ? S[i * ld + col] : cmake(0.0, 0.0));
+          const cplx v1 = cmul(xr[i + 1], col < b ? S[(i + 1) * ld + col] : cmake(0.0, 0.0));
+          acc.x -= v0.x; acc.y -= v0.y;
+          acc2.x -= v1.x; acc2.y -= v1.y;
+        }
+        acc.x += acc2.x; acc.y += acc2.y;
+      }
+      tr[c] = acc;
+      __syncwarp();
+      cplx x = cmake(0.0, 0.0);
+      const cplx* X = Xs + pb * CNB * CNB;
+#pragma unroll
+      for (int cp = 0; cp < CNB; ++cp)
+        if (cp <= c) x = cfma(tr[cp], X[cp * CNB + c], x);
+      __syncwarp();
+      if (col < b) xr[col] = x;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  {
+    cplx* Out = cb + g.Out;
+    for (int r = wp; r < rl; r += nw) {
+      if (r0 + r >= g.rows) break;
+      for (int c = lane; c < b; c += 32) Out[(long long)(r0 + r) * b + c] = Ys[r * ld + c];
+    }
+  }
+}
+
+static size_t cholqr_cluster_smem(int b, int rl) {
+  const int ld = b + 1, nblk = (b + CNB - 1) / CNB;
+  return sizeof(double2) * ((size_t)b * ld + (size_t)rl * ld + (size_t)nblk * CNB * CNB + 32 * 17) + 3 * sizeof(double) * (size_t)b + 64;
+}
+
+// rows per CTA (0: shape not handled by the cluster kernel)
+static int cholqr_cluster_rl(int64_t rows, int b) {
+  static const bool on = !(getenv("KBP_CHOLQR_CLUSTER") && atoi(getenv("KBP_CHOLQR_CLUSTER")) == 0);
+  if (!on) return 0;
+  for (int rl = 64; rl >= 32; rl >>= 1) {
+    if ((rows + rl - 1) / rl > 8) continue;
+    if (cholqr_cluster_smem(b, rl) > 225 * 1024) continue;
+    // the all-reduce keeps at most 4 entries per thread in registers
+    const int C = (int)((rows + rl - 1) / rl);
+    if (((int64_t)b * (b + 1) + C - 1) / C > 4 * 512) continue;
+    return rl;
+  }
+  return 0;
 }
 
 // Out (rows x b) = Y R^{-1} for upper-triangular R by block forward substitution over the 16-column panels:
@@ -542,6 +743,35 @@ void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, i
 constexpr int GRAM_SPLIT = 4;
 
 static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat) {
+  if (const int rl = cholqr_cluster_rl(rows, b)) {
+    CholQrArgs g{Y, T, R_out, (int)rows, b, rl, a.mask, a.mask_want};
+    const int C = (int)((rows + rl - 1) / rl);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C, (unsigned)a.nb);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = cholqr_cluster_smem(b, rl);
+    cfg.stream = a.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, cholqr_cluster_kernel, a.base, (long long)a.chain_stride, g, stat);
+    if (le == cudaSuccess) {
+      ++*a.launches;
+      PM(2);
+      return T;
+    }
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      fprintf(stderr, "[kbp] cholqr_cluster_kernel launch refused (%s; rows %lld b %d cluster %d smem %zu): three-kernel path\n", cudaGetErrorString(le),
+              (long long)rows, b, C, (size_t)cfg.dynamicSmemBytes);
+    }
+    cudaGetLastError();                         // cluster launch refused: three-kernel path
+  }
   const int split = rows >= 256 ? GRAM_SPLIT : 1;
   gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
   PM(1);
@@ -729,7 +959,15 @@ static void tsvd_more_round(const Arena& a, const TsvdBufs& w, int64_t A, int64_
 int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
                           int nr_bulk, int slot_lognorm, int slot_trunc, int b) {
   static const bool debug = getenv("KBP_SVD_DEBUG") != nullptr;
-  static const int it_cold = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
+  static const int it_default = getenv("KBP_TSVD_IT0") ? atoi(getenv("KBP_TSVD_IT0")) : 7;
+  static const bool learn = !(getenv("KBP_TSVD_LEARN") && atoi(getenv("KBP_TSVD_LEARN")) == 0);
+  // An op that needed r > 1 rounds when its program ran host-driven (previous BP iteration: nearly the same spectrum) gets
+  // the iterations of those rounds up front in the captured graph: one Rayleigh-Ritz step + check instead of r.
+  int it_cold = it_default;
+  if (learn && a0.capture && a0.tsvd_rounds) {
+    auto f = a0.tsvd_rounds->find(a0.op_key);
+    if (f != a0.tsvd_rounds->end() && f->second > 1) it_cold = it_default + ((f->second < 4 ? f->second : 4) - 1) * TSVD_IT_MORE;
+  }
   // cold start: after `safe0` SAFE iterations the block is already ordered well enough (contamination of column j by a
   // larger direction i has decayed as (s_j/s_i)^(2k), one fast step amplifies it by (s_i/s_j)^2) for the FAST form
   static const int safe0 = getenv("KBP_TSVD_SAFE0") ? atoi(getenv("KBP_TSVD_SAFE0")) : 2;
@@ -844,10 +1082,12 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
     body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
     if (svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc) < 0) return -1;
   }
+  if (!a.capture && a.tsvd_rounds) (*a.tsvd_rounds)[a.op_key] = rounds;
   return rounds;
 }
 
 void init_tsvd_attributes() {
+  cudaFuncSetAttribute(cholqr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + static shared memory <= 227 KB
   cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
 }

@@ -35,6 +35,7 @@ struct kbp_ctx {
   cudaStream_t body_stream[2] = {nullptr, nullptr};   // capture streams of conditional-node bodies
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; bool bad = false; };
   std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of whole programs, keyed by a hash of the op stream
+  std::unordered_map<unsigned long long, int> tsvd_rounds;
   int64_t graph_replays = 0;
   int64_t graph_captures = 0;
   int64_t graph_min_words = 256;         // shorter programs (one-off algebra of the ITE step) run as plain launches
@@ -329,7 +330,7 @@ static inline double bits_to_double(int64_t b) {
   return d;
 }
 
-static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph);
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph, uint64_t phash);
 
 static uint64_t program_hash(const int64_t* w, int64_t n_words) {
   uint64_t h = 1469598103934665603ull;
@@ -365,11 +366,11 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   static const bool sync_every = getenv("KBP_SYNC_EVERY_OP") != nullptr;
   static const bool env_first = getenv("KBP_GRAPH_FIRST") != nullptr && atoi(getenv("KBP_GRAPH_FIRST")) != 0;
   const bool capture_first = env_first || c->graph_first;
-  if (!graphs_on || c->profile || sync_every || n_words < c->graph_min_words) return run_ops(c, w, n_words, false, nullptr);
   const uint64_t h = program_hash(w, n_words);
+  if (!graphs_on || c->profile || sync_every || n_words < c->graph_min_words) return run_ops(c, w, n_words, false, nullptr, h);
   auto it = c->graphs.find(h);
   if (it == c->graphs.end()) {
-    if (c->graphs.size() >= KBP_GRAPH_MAX) return run_ops(c, w, n_words, false, nullptr);
+    if (c->graphs.size() >= KBP_GRAPH_MAX) return run_ops(c, w, n_words, false, nullptr, h);
     it = c->graphs.emplace(h, kbp_ctx::GraphEntry()).first;
   }
   kbp_ctx::GraphEntry& ge = it->second;
@@ -381,7 +382,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
     ++c->graph_replays;
     return KBP_OK;
   }
-  if (ge.bad || (ge.seen++ == 0 && !capture_first)) return run_ops(c, w, n_words, false, nullptr);
+  if (ge.bad || (ge.seen++ == 0 && !capture_first)) return run_ops(c, w, n_words, false, nullptr, h);
   const int64_t l0 = c->launches;
   int64_t c0[8];
   for (int k = 0; k < 8; ++k) c0[k] = c->counters[k];
@@ -391,7 +392,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
     c->launches = l0;
     for (int k = 0; k < 8; ++k) c->counters[k] = c0[k];
     fprintf(stderr, "[kbp] graph capture of a %lld-word program failed (%s): running it with host-driven loops\n", (long long)n_words, why);
-    return run_ops(c, w, n_words, false, nullptr);
+    return run_ops(c, w, n_words, false, nullptr, h);
   };
   if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return give_up("begin capture");
   cudaStreamCaptureStatus st;
@@ -400,7 +401,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   const cudaGraphNode_t* deps = nullptr;
   size_t nd = 0;
   int rc = KBP_E_CUDA;
-  if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &top, &deps, &nd) == cudaSuccess && top) rc = run_ops(c, w, n_words, true, top);
+  if (cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &top, &deps, &nd) == cudaSuccess && top) rc = run_ops(c, w, n_words, true, top, h);
   cudaGraph_t graph = nullptr;
   const cudaError_t e1 = cudaStreamEndCapture(c->stream, &graph);
   if (rc != KBP_OK || e1 != cudaSuccess || !graph) {
@@ -422,7 +423,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   return KBP_OK;
 }
 
-static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph) {
+static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, cudaGraph_t top_graph, uint64_t phash) {
   if (!c || !c->arena || !w) return fail(c, KBP_E_ARG, "kbp_run: arena not reserved");
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
@@ -431,6 +432,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, 
   a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
   a.ctl = c->ctl; a.ctl_host = c->ctl_host; a.chain_state = reinterpret_cast<int*>(c->ctl + 1);
   a.mask = nullptr; a.mask_want = 0;
+  a.tsvd_rounds = &c->tsvd_rounds; a.op_key = 0;
   a.capture = capture; a.top_graph = top_graph; a.body_stream[0] = c->body_stream[0]; a.body_stream[1] = c->body_stream[1]; a.depth = 0;
   const int64_t E = c->chain_elems;
   auto in_arena = [&](int64_t off, int64_t n) { return off >= 0 && n >= 0 && off + n <= E; };
@@ -488,6 +490,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, 
       }
       case KBP_OP_SVD: {
         NEED(11);
+        a.op_key = phash ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1));
         const int64_t A = w[i + 1], US = w[i + 2], Vh = w[i + 3], wk = w[i + 4], m = w[i + 5], n = w[i + 6], keep = w[i + 7];
         const int64_t nrb = w[i + 8], s0 = w[i + 9], s1 = w[i + 10], warm = w[i + 11];
         if (m <= 0 || n <= 0 || keep <= 0 || keep > (m < n ? m : n) || !slot_ok(s0) || !slot_ok(s1)) BAD("svd: bad argument");

@@ -50,6 +50,10 @@ struct Arena {
   int mask_want;
   // whole-program stream capture in progress: data-dependent loops become conditional graph nodes whose bodies are captured
   // on body_stream[depth]; conditional handles are created on top_graph
+  // rounds the subspace iteration of each SVD op needed in the host-driven run of its program (key: program hash ^ word
+  // index of the op): the captured graph gives such an op its iterations up front and does the Rayleigh-Ritz step once
+  std::unordered_map<unsigned long long, int>* tsvd_rounds;
+  unsigned long long op_key;
   bool capture;
   cudaGraph_t top_graph;
   cudaStream_t body_stream[2];

@@ -41,7 +41,15 @@ def dense_rel_diff(a_mps, b_mps, with_factor=True):
     return float(np.linalg.norm(a * ph - b) / np.linalg.norm(a))
 
 
+def _unit_sites(m):
+    """the same state with every site scaled to unit Frobenius norm (long chains under- / overflow otherwise)."""
+    r = mps_np.MPS(m.N)
+    r.A = [np.asarray(a) / np.linalg.norm(a) for a in m.A]
+    return r
+
+
 def overlap_defect(a_mps, b_mps):
+    a_mps, b_mps = _unit_sites(a_mps), _unit_sites(b_mps)
     ab = mps_np.mps_inner_product(a_mps, b_mps, True)
     aa = mps_np.mps_inner_product(a_mps, a_mps, True)
     bb = mps_np.mps_inner_product(b_mps, b_mps, True)

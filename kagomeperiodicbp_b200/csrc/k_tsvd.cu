@@ -74,7 +74,10 @@ thread_local CatProf t_prof;
 #define PM(cat) t_prof.mark(a.stream, cat)
 
 
-constexpr int TSVD_BMAX = 112;            // b x b complex must fit one CTA's shared memory (chol + small SVD)
+constexpr int TSVD_BMAX = 112;            // widest block whose b x b Cholesky fits one CTA's shared memory
+constexpr int TSVD_BMAX2 = 192;           // widest block at all: two column blocks orthogonalised by block Gram-Schmidt (D = 6:
+                                          // keep 72 / 82 -> b = 184 / 192), Rayleigh-Ritz SVD on the cluster Jacobi kernel
+constexpr int TSVD_B1 = 96;               // first column block of a wide panel
 constexpr double TSVD_RES_TOL = 2e-13;
 constexpr double TSVD_PIVOT_DEAD = 1e-13;  // pivot / diagonal below this: the column is numerically dependent -> dropped
 // Dropped directions carry at most ~3e-7 of a column's norm (pivot ratio 1e-13), i.e. singular values below 3e-7 s_1.
@@ -85,17 +88,20 @@ constexpr double TSVD_MIN_RATIO = 1e-6;
 static inline int64_t rup8(int64_t x) { return (x + 7) / 8 * 8; }
 
 int tsvd_block(int64_t m, int64_t n, int64_t keep) {
-  static const int factor_x10 = getenv("KBP_TSVD_FACTOR_X10") ? atoi(getenv("KBP_TSVD_FACTOR_X10")) : 25;
+  // block = 2.0 x keep.  Measured on the D=4, N=3 side program (B200, whole program as one graph, profiles/r02_SUMMARY.md):
+  // 1.5 -> 136 ms, 1.7 -> 122, 2.0 -> 112.5, 2.2 -> 132, 2.5 -> 133, 3.0 -> 151 per chain: a wider block saves iterations
+  // (8.0 at 2.5 vs 9.6 at 2.0 on average) but every b x b kernel of an iteration (Cholesky, Jacobi, triangular solve) gets slower
+  static const int factor_x10 = getenv("KBP_TSVD_FACTOR_X10") ? atoi(getenv("KBP_TSVD_FACTOR_X10")) : 20;
   const int64_t p = m < n ? m : n;
   int64_t b = rup8(keep * factor_x10 / 10);
-  if (b > TSVD_BMAX) b = TSVD_BMAX;
+  if (b > TSVD_BMAX2) b = TSVD_BMAX2;
   if (b < keep + 8 || b * 100 > p * 80) return 0;     // not worth it / not applicable
   return (int)b;
 }
 
 int64_t tsvd_work_elems(int64_t m, int64_t n) {
-  const int64_t q = m < n ? n : m, b = TSVD_BMAX;
-  return 4 * rup8(q) * b + 17 * b * b + m * n + 64;
+  const int64_t q = m < n ? n : m, b = TSVD_BMAX2;
+  return 6 * rup8(q) * b + 17 * b * b + m * n + 64;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -505,7 +511,10 @@ static size_t cholqr_cluster_smem(int b, int rl) {
 
 // rows per CTA (0: shape not handled by the cluster kernel)
 static int cholqr_cluster_rl(int64_t rows, int b) {
-  static const bool on = !(getenv("KBP_CHOLQR_CLUSTER") && atoi(getenv("KBP_CHOLQR_CLUSTER")) == 0);
+  // opt-in (KBP_CHOLQR_CLUSTER=1): one launch instead of three, but measured SLOWER on the B200 (118 us against 17 + 56 + 21 us at
+  // b = 80: the slab Gram and the in-place solve are bound by the shared-memory pipe of the 8 SMs a cluster has, where the
+  // split-K Gram GEMM and the 16-CTA solve spread over the chip); kept for the DMMA version of its Gram stage
+  static const bool on = getenv("KBP_CHOLQR_CLUSTER") && atoi(getenv("KBP_CHOLQR_CLUSTER")) != 0;
   if (!on) return 0;
   for (int rl = 64; rl >= 32; rl >>= 1) {
     if ((rows + rl - 1) / rl > 8) continue;
@@ -737,12 +746,49 @@ __global__ void tsvd_fill_kernel(double* p, int n, double v) {
 void svd_small(const Arena& a, int64_t A, int64_t lda, int64_t US, int64_t Vh, int64_t m, int64_t n, int64_t keep, int nr_bulk,
                int slot_lognorm, int slot_trunc);
 
+// dst (rows x w, contiguous) = src[:, c0 : c0 + w] of a rows x ld matrix
+__global__ void tsvd_gather_cols_kernel(cplx* __restrict__ base, long long chain_stride, long long dst_, long long src_, int rows, int ld, int c0, int w,
+                                        const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const long long total = (long long)rows * w;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / w;
+    const int c = (int)(e - r * w);
+    cb[dst_ + e] = cb[src_ + r * ld + c0 + c];
+  }
+}
+// dst[:, c0 : c0 + w] (rows x ld) = src (rows x w, contiguous);  zero_rest: the other columns of those rows are zeroed
+__global__ void tsvd_scatter_cols_kernel(cplx* __restrict__ base, long long chain_stride, long long dst_, long long src_, int rows, int ld, int c0, int w,
+                                         const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  const long long total = (long long)rows * w;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / w;
+    const int c = (int)(e - r * w);
+    cb[dst_ + r * ld + c0 + c] = cb[src_ + e];
+  }
+}
+// x -= y  (n elements)
+__global__ void tsvd_sub_kernel(cplx* __restrict__ base, long long chain_stride, long long x_, long long y_, long long n, const int* __restrict__ mask,
+                                int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) cb[x_ + e] = csub(cb[x_ + e], cb[y_ + e]);
+}
+
+static inline int grid1d(long long n) {
+  long long g = (n + 255) / 256;
+  return (int)(g > 148 * 8 ? 148 * 8 : (g < 1 ? 1 : g));
+}
+
 // Y (rows x b) <- Y Rinv with G = Y^H Y = R^H R.  `T` is a rows x b scratch; returns the buffer holding the result
 // (Y and T swap roles).  R_out >= 0: also store R.  The Gram matrix is accumulated as GRAM_SPLIT partial sums over
 // row ranges (more CTAs on a product whose output is only b x b) which the Cholesky kernel adds up.
 constexpr int GRAM_SPLIT = 4;
 
-static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat) {
+static int64_t cholqr_pass_narrow(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat) {
   if (const int rl = cholqr_cluster_rl(rows, b)) {
     CholQrArgs g{Y, T, R_out, (int)rows, b, rl, a.mask, a.mask_want};
     const int C = (int)((rows + rl - 1) / rl);
@@ -787,6 +833,42 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
     trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b, a.mask, a.mask_want);
     ++*a.launches;
     PM(3);
+  }
+  return T;
+}
+
+// Wide panels (b > TSVD_BMAX): the b x b Cholesky no longer fits one CTA's shared memory.  The panel is split into two column
+// blocks Y = [Y1 | Y2] (b1 = 96 columns, the rest) orthogonalised by block Gram-Schmidt with a Cholesky-QR per block:
+//     Y1 = Q1 R11,   R12 = Q1^H Y2,   Y2 - Q1 R12 = Q2 R22        ->   Y = [Q1 | Q2] [[R11, R12], [0, R22]]
+// (the callers repeat the pass on the last iteration, which makes it block classical Gram-Schmidt with reorthogonalisation).
+// `X` = scratch of >= 2 * rows * b + 2 * b * b elements (panels 4 and 5 of the workspace).
+static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int64_t Dinv, int64_t R_out, int64_t rows, int b, double* stat, int64_t X = -1) {
+  if (b <= TSVD_BMAX) return cholqr_pass_narrow(a, Y, T, Gp, Dinv, R_out, rows, b, stat);
+  const int b1 = TSVD_B1, b2 = b - b1;
+  const int64_t Y1 = X, Y2 = Y1 + rows * b1, Q1 = Y2 + rows * b2, Q2 = Q1 + rows * b1, R11 = Q2 + rows * b2, R22 = R11 + (int64_t)b1 * b1,
+                R12 = R22 + (int64_t)b2 * b2, P2 = Y1;                        // Y1 is dead once Q1 exists: reused for Q1 R12
+  const dim3 g1(grid1d(rows * b1), a.nb), g2(grid1d(rows * b2), a.nb);
+  tsvd_gather_cols_kernel<<<g1, 256, 0, a.stream>>>(a.base, a.chain_stride, Y1, Y, (int)rows, b, 0, b1, a.mask, a.mask_want);
+  tsvd_gather_cols_kernel<<<g2, 256, 0, a.stream>>>(a.base, a.chain_stride, Y2, Y, (int)rows, b, b1, b2, a.mask, a.mask_want);
+  *a.launches += 2;
+  cholqr_pass_narrow(a, Y1, Q1, Gp, Dinv, R11, rows, b1, stat);
+  gemm(a, R12, Q1, Y2, b1, b2, rows, OP_C, OP_N);                           // R12 = Q1^H Y2
+  gemm(a, P2, Q1, R12, rows, b2, b1, OP_N, OP_N);                           // Q1 R12
+  tsvd_sub_kernel<<<g2, 256, 0, a.stream>>>(a.base, a.chain_stride, Y2, P2, rows * b2, a.mask, a.mask_want);
+  ++*a.launches;
+  cholqr_pass_narrow(a, Y2, Q2, Gp, Dinv, R22, rows, b2, stat);
+  if (T >= 0) {
+    tsvd_scatter_cols_kernel<<<g1, 256, 0, a.stream>>>(a.base, a.chain_stride, T, Q1, (int)rows, b, 0, b1, a.mask, a.mask_want);
+    tsvd_scatter_cols_kernel<<<g2, 256, 0, a.stream>>>(a.base, a.chain_stride, T, Q2, (int)rows, b, b1, b2, a.mask, a.mask_want);
+    *a.launches += 2;
+  }
+  if (R_out >= 0) {                                                          // assemble the b x b factor (rows b1.. of the left block are zero)
+    zero(a, R_out, (int64_t)b * b);
+    tsvd_scatter_cols_kernel<<<dim3(grid1d(b1 * b1), a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, R_out, R11, b1, b, 0, b1, a.mask, a.mask_want);
+    tsvd_scatter_cols_kernel<<<dim3(grid1d(b1 * b2), a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, R_out, R12, b1, b, b1, b2, a.mask, a.mask_want);
+    tsvd_scatter_cols_kernel<<<dim3(grid1d(b2 * b2), a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, R_out + (int64_t)b1 * b, R22, b2, b, b1, b2, a.mask,
+                                                                               a.mask_want);
+    *a.launches += 3;
   }
   return T;
 }
@@ -882,6 +964,7 @@ static cudaError_t read_ctl(const Arena& a) {
 struct TsvdBufs {
   int64_t panel[4];                  // four q x b panels
   int64_t Gp, Ri, Rs, R1, R2, Rm, Vbs, Tk, Pb;
+  int64_t X;                         // scratch of the wide-panel Cholesky-QR (two panels + b x b)
 };
 
 // Rayleigh-Ritz on span(Q), the kept factors, and the two check kernels.  Q in panel `Qb`, `f0`, `f1` free panels.
@@ -897,11 +980,11 @@ static void rayleigh_ritz_and_check(const Arena& a, const TsvdBufs& w, int64_t A
   PM(0);
   int64_t Rsmall;
   if (single_pass) {
-    cholqr_pass(a, f0, -1, w.Gp, w.Ri, w.R1, m, b, stat);           // W = Y R1
+    cholqr_pass(a, f0, -1, w.Gp, w.Ri, w.R1, m, b, stat, w.X);           // W = Y R1
     Rsmall = w.R1;
   } else {
-    cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.R1, m, b, stat);
-    cholqr_pass(a, f1, -1, w.Gp, w.Ri, w.R2, m, b, stat);
+    cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.R1, m, b, stat, w.X);
+    cholqr_pass(a, f1, -1, w.Gp, w.Ri, w.R2, m, b, stat, w.X);
     gemm(a, w.Rm, w.R2, w.R1, b, b, b, OP_N, OP_N);                 // W = Y (R2 R1)
     PM(5);
     Rsmall = w.Rm;
@@ -937,7 +1020,7 @@ static void tsvd_more_round(const Arena& a, const TsvdBufs& w, int64_t A, int64_
     gemm(a, f0, A, cur, m, b, n, OP_N, OP_N);                       // W = A Q
     gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                        // Z = A^H W
     PM(0);
-    cholqr_pass(a, f1, other, w.Gp, w.Ri, w.Rs, n, b, stat);        // Q = orth(Z) -> other
+    cholqr_pass(a, f1, other, w.Gp, w.Ri, w.Rs, n, b, stat, w.X);        // Q = orth(Z) -> other
     const int64_t t = cur; cur = other; other = t;
   }
   // TSVD_IT_MORE odd: cur == Qb again
@@ -982,6 +1065,7 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   TsvdBufs w;
   int64_t o = work;
   for (int i = 0; i < 4; ++i) { w.panel[i] = o; o += qp * b; }
+  w.X = o; o += b > TSVD_BMAX ? 2 * qp * b + bb : 0;
   w.Gp = o; o += GRAM_SPLIT * bb;
   w.Ri = o; o += bb;      // 1 / diagonal of the last Cholesky factor (b entries) + the inverses of its diagonal blocks
   w.Rs = o; o += bb;      // the last Cholesky factor when the caller does not keep it
@@ -1023,15 +1107,15 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
       }
       gemm(a, f1, A, f0, n, b, m, OP_C, OP_N);                        // Z = A^H W        -> f1
       PM(0);
-      cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat);           // orth(Z)          -> f0
-      if (done + 1 == it_cold) { cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat); replace_q(f1); }   // twice on the last one
+      cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat, w.X);           // orth(Z)          -> f0
+      if (done + 1 == it_cold) { cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat, w.X); replace_q(f1); }   // twice on the last one
       else replace_q(f0);
     } else {
-      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, m, b, stat);           // Y = orth(W)      -> f1
+      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, m, b, stat, w.X);           // Y = orth(W)      -> f1
       gemm(a, f0, A, f1, n, b, m, OP_C, OP_N);                        // Z = A^H Y        -> f0
       PM(0);
-      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat);           // orth(Z)          -> f1
-      if (done + 1 == it_cold) { cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat); replace_q(f0); }   // twice on the last one
+      cholqr_pass(a, f0, f1, w.Gp, w.Ri, w.Rs, n, b, stat, w.X);           // orth(Z)          -> f1
+      if (done + 1 == it_cold) { cholqr_pass(a, f1, f0, w.Gp, w.Ri, w.Rs, n, b, stat, w.X); replace_q(f0); }   // twice on the last one
       else replace_q(f1);
     }
   }

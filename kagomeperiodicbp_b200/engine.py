@@ -93,7 +93,7 @@ def svd_work_elems(m: int, n: int) -> int:
     p_pad = (p + 31) // 32 * 32
     q_pad = (q + 7) // 8 * 8
     jacobi = p_pad * (q_pad + p_pad)
-    subspace = 4 * q_pad * 112 + 17 * 112 * 112 + m * n + 64      # k_tsvd.cu: tsvd_work_elems
+    subspace = 6 * q_pad * 192 + 17 * 192 * 192 + m * n + 64      # k_tsvd.cu: tsvd_work_elems
     return max(jacobi, subspace)
 
 

@@ -20,10 +20,11 @@ def _cell_from(g):
     return UnitCell(g["A"], g["B"], g["C"])
 
 
-@pytest.mark.parametrize("D,N", [(2, 2), (2, 3), (3, 2), (3, 3), (4, 2), (4, 3)])
+@pytest.mark.parametrize("D,N", [(2, 2), (2, 3), (3, 2), (3, 3), (4, 2), (4, 3), (6, 2)])
 def test_chain_vs_golden_reference(D, N):
     """one ToMessage bubblecon call per side, uniform messages: device result vs the REFERENCE's own output
-    (D=4: the benchmarked bond dimension; the N=3 fixture holds two of the six sides to bound its size)."""
+    (D=4: the benchmarked bond dimension; the N=3 fixture holds two of the six sides to bound its size;
+    D=6, chi_bp=72: BASELINE config C4 -- 2592 x 2592 truncations on the wide-block subspace path, one side)."""
     g = golden(f"chain_D{D}_N{N}.npz")
     cell = _cell_from(g)
     tn = bp.KagomeTNRepeatedUnitCell(cell, N)

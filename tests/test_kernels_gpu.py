@@ -198,6 +198,26 @@ def test_normalize_embed_eye(eng):
     assert np.array_equal(e, np.eye(6))
 
 
+@pytest.mark.parametrize("m,n,keep", [(800, 800, 72), (1296, 648, 82)])
+def test_svd_subspace_wide_block_two_column_blocks(eng, m, n, keep):
+    """keep = 72 / 82 (chi_bp and chi at D = 6): block of 144 / 168 columns, wider than one CTA's Cholesky takes -- the panel is
+    orthogonalised as two column blocks (block Gram-Schmidt + Cholesky-QR per block)."""
+    a = rnd(m, n)
+    u, s, vh = np.linalg.svd(a, full_matrices=False)
+    s = np.exp(-0.04 * np.arange(len(s)))
+    a = (u * s) @ vh
+    before = eng.svd_counters()
+    res, sl = run(eng, lambda p, t: list(p.svd_trunc(t[0], keep, True, 0, 1)), [[a]])
+    after = eng.svd_counters()
+    assert after["subspace"] == before["subspace"] + 1 and after["subspace_fallback"] == before["subspace_fallback"], (before, after)
+    us, v = res[0]
+    ref = (u[:, :keep] * s[:keep]) @ vh[:keep]
+    gap = (s[keep - 1] - s[keep]) / s[0]
+    assert np.linalg.norm(us @ v * np.linalg.norm(s) - ref) <= 2e-13 * np.linalg.norm(s) / gap
+    assert np.linalg.norm(v @ v.conj().T - np.eye(keep)) <= 1e-12
+    assert abs(sl[0, 1] - np.sqrt(np.sum(s[keep:] ** 2) / np.sum(s ** 2))) <= 1e-10 and sl[0, -1] == 0
+
+
 def test_svd_subspace_widest_block(eng):
     """keep = 42 (chi = 2 D^2 + 10 at D = 4: the ToCore / ToEdge chains) runs the subspace path with the widest block the
     b x b kernels take (112): their shared-memory footprints must fit."""

@@ -165,6 +165,8 @@ if __name__ == "__main__":
         make_chain(4, 2, args.check)
         make_bp(4, 2, 0.1, args.check)
         make_chain(4, 3, args.check, sides=("D", "UR"))
+    if args.only == "d6":       # config C4 (chi_bp = 72): one side, tens of minutes of LAPACK on 2592 x 2592 matrices
+        make_chain(6, 2, args.check, sides=("D",))
     if args.only in ("", "bp"):
         make_bp(2, 2, None, args.check)
         make_bp(2, 2, 0.1, args.check)

@@ -124,9 +124,36 @@ __global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ 
   }
 }
 
+bool qr_cluster_fits(int64_t m, int64_t n);
+
+// Tall matrices the cluster kernel does not take (1024 x 64 at D = 4, 2592 x 72 at D = 6): TSQR.  The rows are cut into
+// nbk blocks that it does take, A_i = Q_i R_i; the stacked R_i (nbk n x n) are factored again, [R_1; ...; R_nbk] = Qs R; then
+// Q rows of block i = Q_i Qs_i.  Householder at both levels: orthonormal Q also for rank-deficient input.
+static bool qr_tsqr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
+  if (m < 2 * n) return false;
+  for (int nbk = 2; nbk <= 8; ++nbk) {
+    const int64_t mb = (m + nbk - 1) / nbk, last = m - mb * (nbk - 1);
+    if (last < n || 4 * nbk * n > m) break;
+    if (!qr_cluster_fits(mb, n) || !qr_cluster_fits(last, n) || !qr_cluster_fits(nbk * n, n)) continue;
+    const int64_t T = work, S = T + m * n, Qs = S + nbk * n * n, W2 = Qs + nbk * n * n;
+    for (int i = 0; i < nbk; ++i) {
+      const int64_t rows = i + 1 < nbk ? mb : last;
+      if (!qr_cluster(a, A + i * mb * n, T + i * mb * n, S + i * n * n, rows, n)) return false;   // (nothing launched yet if i == 0)
+    }
+    qr(a, S, Qs, R, W2, nbk * n, n);
+    for (int i = 0; i < nbk; ++i) {
+      const int64_t rows = i + 1 < nbk ? mb : last;
+      gemm(a, Q + i * mb * n, T + i * mb * n, Qs + i * n * n, rows, n, n, OP_N, OP_N);
+    }
+    return true;
+  }
+  return false;
+}
+
 void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   if (m == 0 || n == 0) return;
   if (qr_cluster(a, A, Q, R, m, n)) return;                // shared-memory resident, rows over a cluster (k_qr_cluster.cu)
+  if (qr_tsqr(a, A, Q, R, work, m, n)) return;
   qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n);
   ++*a.launches;
 }

@@ -262,6 +262,15 @@ size_t qrc_smem(int m, int n, int C) {
 
 }  // namespace
 
+// does the cluster kernel take this shape?
+bool qr_cluster_fits(int64_t m, int64_t n) {
+  static const bool on = !(getenv("KBP_QR_CLUSTER") && atoi(getenv("KBP_QR_CLUSTER")) == 0);
+  if (!on || m > 8 * QRC_MLOC_MAX || n > 256) return false;
+  int C = 1;
+  while (C <= 8 && ((m + C - 1) / C > QRC_MLOC_MAX || qrc_smem((int)m, (int)n, C) > QRC_SMEM_MAX)) C <<= 1;
+  return C <= 8;
+}
+
 // returns false if the shape is not handled here (caller uses the one-CTA kernel)
 bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int64_t n) {
   static const bool on = !(getenv("KBP_QR_CLUSTER") && atoi(getenv("KBP_QR_CLUSTER")) == 0);

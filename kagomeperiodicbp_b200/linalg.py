@@ -169,9 +169,10 @@ class RArr:
 
 
 class ResidentBackend:
-    """eager device execution with a persistent arena: every call appends a few ops to one growing tensor program and
-    launches them asynchronously on the context's stream; buffers are recycled by the program's first-fit allocator when
-    their Python handles die (all work is stream-ordered, so reuse is safe).  Host <-> device traffic is limited to the
+    """device execution with a persistent arena: every call appends a few ops to one growing tensor program; the queued ops are
+    launched (one kbp_run, asynchronous on the context's stream) only when the host needs a value -- ``to_host``, ``norm``, the
+    singular values of ``svd`` / ``eigh`` -- or uploads one (``put``).  Buffers are recycled by the program's first-fit
+    allocator when their Python handles die (all work is stream-ordered, so reuse is safe).  Host <-> device traffic is limited to the
     inputs (unit-cell tensors, ring tensors of the ToCore chains), small matrices built on the host (diag(sqrt(S)), ...)
     and the results that host code actually looks at."""
 
@@ -227,9 +228,7 @@ class ResidentBackend:
     def transpose(self, a, perm):
         if not isinstance(a, RArr):
             return np.transpose(np.asarray(a), perm)
-        out = RArr(self, self.p.transpose(a.dt, perm))
-        self._flush()
-        return out
+        return RArr(self, self.p.transpose(a.dt, perm))
 
     # ---------------------------------------------------------------- device ops
     def tensordot(self, a, b, axes, conj_a=False, conj_b=False):
@@ -241,15 +240,12 @@ class ResidentBackend:
         else:
             ax = (tuple(int(x) for x in axes[0]), tuple(int(x) for x in axes[1]))
             out = RArr(self, self.p.tensordot(A, Bt, ax, conj_a=conj_a, conj_b=conj_b))
-        self._flush()
         return out
 
     def scale(self, a, s):
         A = self._dt(a)
         c = self.p.matmul(A.reshape(A.size, 1), self.put(np.array([[s]], dtype=np.complex128)).dt, A.size, 1, 1)
-        out = RArr(self, c.reshape(A.shape))
-        self._flush()
-        return out
+        return RArr(self, c.reshape(A.shape))
 
     def lincomb(self, a, alpha, b, beta):
         A, Bt = self._dt(a), self._dt(b)
@@ -260,9 +256,7 @@ class ResidentBackend:
         z = self.p.zeros((r, 1, 2 * c))
         self.p.embed(z, (0, 0, 0), A.reshape(r, 1, c))
         self.p.embed(z, (0, 0, c), Bt.reshape(r, 1, c))
-        out = RArr(self, self.p.matmul(z.reshape(r, 2 * c), coef.dt, r, c, 2 * c).reshape(shape))
-        self._flush()
-        return out
+        return RArr(self, self.p.matmul(z.reshape(r, 2 * c), coef.dt, r, c, 2 * c).reshape(shape))
 
     def hermitize(self, m):
         M = self._dt(m)
@@ -285,7 +279,6 @@ class ResidentBackend:
 
     def qr(self, m):
         q, r = self.p.qr(self._dt(m))
-        self._flush()
         return RArr(self, q), RArr(self, r)
 
     def _svd_raw(self, m):

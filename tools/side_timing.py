@@ -10,11 +10,12 @@ from kagomeperiodicbp_b200.lattice import BLOCK_SIDES_CCW
 from kagomeperiodicbp_b200.runtime import get_engine
 
 D, N = int(sys.argv[1]), int(sys.argv[2])
+B = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 1        # unit cells batched into every launch
 cfg = BPConfig(trunc_dim=2 * D * D, msg_diff_terminate=1e-6, damping=0.1, init_msg="UQ")
 cell = UnitCell.random(2, D, seed=0)
 msgs = bp.initial_messages(D, N, "UQ")
 cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", f"msgs_D{D}_N{N}.npz")
-if "--one-plain" in sys.argv and os.path.exists(cache):      # steady-state messages of an earlier run: nothing else gets profiled
+if os.path.exists(cache):      # steady-state messages of an earlier run: nothing else gets profiled
     from kagomeperiodicbp_b200.containers import Message
     from kagomeperiodicbp_b200.mps import MPS
     z = np.load(cache)
@@ -28,8 +29,8 @@ shapes = bp._msg_shapes(msgs)
 comps = {s: bp.compile_side_program(N, 2, D, s, 2 * D * D, shapes, 0.1) for s in BLOCK_SIDES_CCW}
 engs = {s: get_engine(("side", s), 0) for s in BLOCK_SIDES_CCW}
 for s in BLOCK_SIDES_CCW:
-    comps[s].load(engs[s], 1)
-    engs[s].upload(0, comps[s].pack_inputs([bp._side_inputs(cell, msgs, comps[s])]))
+    comps[s].load(engs[s], B)
+    engs[s].upload(0, comps[s].pack_inputs([bp._side_inputs(cell, msgs, comps[s])] * B))
     engs[s].sync()
 if "--one-plain" in sys.argv:
     t0 = time.perf_counter()
@@ -51,5 +52,5 @@ for k in (1, 2, 3, 6):
         for s in sides:
             engs[s].sync()
         best = min(best, time.perf_counter() - t0)
-    print(f"{k} side(s) concurrently: {best*1e3:.1f} ms per iteration")
+    print(f"{k} side(s) concurrently, {B} cell(s) per launch: {best*1e3:.1f} ms per iteration")
 print(engs["D"].svd_counters())

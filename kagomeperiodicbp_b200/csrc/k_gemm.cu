@@ -46,7 +46,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int BM, int BN, int STAGES, int NWARPS>
+template <int BM, int BN, int STAGES, int NWARPS, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restrict__ base, long long chain_stride, GemmArgs g) {
   constexpr int NTHR = 32 * NWARPS;
   constexpr int WMS = BM / 16, WNS = NWARPS / WMS;    // warp grid
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int wm = w % WMS, wn = w / WMS;
   const int gq = lane >> 2, q = lane & 3;
-  const bool a_kc = (g.opA == OP_N || g.opA == OP_J);   // A stored [m][k]
-  const bool b_kc = (g.opB == OP_T || g.opB == OP_C);   // B stored [n][k]
+  constexpr bool a_kc = A_KC;                           // A stored [m][k]  (opA == N or J)
+  constexpr bool b_kc = B_KC;                           // B stored [n][k]  (opB == T or C)
   const double sa = (g.opA == OP_C || g.opA == OP_J) ? -1.0 : 1.0;
   const double sb = (g.opB == OP_C || g.opB == OP_J) ? -1.0 : 1.0;
 
@@ -79,35 +79,47 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
   if (s_end > slabs_total) s_end = slabs_total;
   const int nslab = s_end > s_begin ? s_end - s_begin : 0;
 
+  // global -> shared copies: every thread owns RA + RB fixed (row, k) positions of a slab.  Source pointers, shared-memory
+  // offsets and row validity are computed ONCE; a slab advances the pointers by a constant (the address arithmetic and
+  // bounds tests per copy were most of the instructions of a small product, whose warps are bound by dependent issue)
+  constexpr int RA = BM * BK / NTHR, RB = BN * BK / NTHR;
+  const cplx* pa[RA];
+  const cplx* pb[RB];
+  int oa[RA], ob[RB], ka[RA], kb[RB];                  // shared offset; k - (k index inside the slab): copy valid iff k0 < ka
+  const long long stepA = a_kc ? BK : (long long)BK * g.m, stepB = b_kc ? BK : (long long)BK * g.n;
+#pragma unroll
+  for (int r = 0; r < RA; ++r) {
+    const int c = t + NTHR * r;
+    const int mm = a_kc ? c / BK : c % BM, kk = a_kc ? c % BK : c / BM;
+    const bool rowok = row0 + mm < g.m;
+    oa[r] = a_kc ? mm * LDK + kk : kk * LDM + mm;
+    ka[r] = rowok ? g.k - kk : 0;
+    pa[r] = Ab + (a_kc ? (long long)(rowok ? row0 + mm : 0) * g.k + (long long)s_begin * BK + kk
+                       : ((long long)s_begin * BK + kk) * g.m + (rowok ? row0 + mm : 0));
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    const int c = t + NTHR * r;
+    const int nn = b_kc ? c / BK : c % BN, kk = b_kc ? c % BK : c / BN;
+    const bool colok = col0 + nn < g.n;
+    ob[r] = b_kc ? nn * LDK + kk : kk * LDN + nn;
+    kb[r] = colok ? g.k - kk : 0;
+    pb[r] = Bb + (b_kc ? (long long)(colok ? col0 + nn : 0) * g.k + (long long)s_begin * BK + kk
+                       : ((long long)s_begin * BK + kk) * g.n + (colok ? col0 + nn : 0));
+  }
   auto issue = [&](int slab, int stage) {
     const int k0 = (s_begin + slab) * BK;
     cplx* at = As + stage * TA;
     cplx* bt = Bs + stage * TB;
 #pragma unroll
-    for (int r = 0; r < BM * BK / NTHR; ++r) {
-      const int c = t + NTHR * r;
-      if (a_kc) {
-        const int mm = c / BK, kk = c % BK;
-        const bool ok = row0 + mm < g.m && k0 + kk < g.k;
-        cp_async16(at + mm * LDK + kk, ok ? Ab + (long long)(row0 + mm) * g.k + k0 + kk : Ab, ok);
-      } else {
-        const int kk = c / BM, mm = c % BM;
-        const bool ok = row0 + mm < g.m && k0 + kk < g.k;
-        cp_async16(at + kk * LDM + mm, ok ? Ab + (long long)(k0 + kk) * g.m + row0 + mm : Ab, ok);
-      }
+    for (int r = 0; r < RA; ++r) {
+      const bool ok = k0 < ka[r];
+      cp_async16(at + oa[r], ok ? pa[r] + slab * stepA : Ab, ok);
     }
 #pragma unroll
-    for (int r = 0; r < BN * BK / NTHR; ++r) {
-      const int c = t + NTHR * r;
-      if (b_kc) {
-        const int nn = c / BK, kk = c % BK;
-        const bool ok = col0 + nn < g.n && k0 + kk < g.k;
-        cp_async16(bt + nn * LDK + kk, ok ? Bb + (long long)(col0 + nn) * g.k + k0 + kk : Bb, ok);
-      } else {
-        const int kk = c / BN, nn = c % BN;
-        const bool ok = col0 + nn < g.n && k0 + kk < g.k;
-        cp_async16(bt + kk * LDN + nn, ok ? Bb + (long long)(k0 + kk) * g.n + col0 + nn : Bb, ok);
-      }
+    for (int r = 0; r < RB; ++r) {
+      const bool ok = k0 < kb[r];
+      cp_async16(bt + ob[r], ok ? pb[r] + slab * stepB : Bb, ok);
     }
   };
 
@@ -222,16 +234,27 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
     }
 }
 
-template <int BM, int BN, int STAGES, int NWARPS>
-static void launch_gemm(const Arena& a, GemmArgs g) {
+template <int BM, int BN, int STAGES, int NWARPS, bool A_KC, bool B_KC>
+static void launch_gemm_l(const Arena& a, GemmArgs g) {
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
   constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
   const unsigned tn = (unsigned)((g.n + BN - 1) / BN), tm = (unsigned)((g.m + BM - 1) / BM);
   g.rows_on_x = tm > tn;
   dim3 grid(g.rows_on_x ? tm : tn, g.rows_on_x ? tn : tm, (unsigned)(a.nb * g.ksplit));
-  zgemm_dmma_kernel<BM, BN, STAGES, NWARPS><<<grid, 32 * NWARPS, smem, a.stream>>>(a.base, a.chain_stride, g);
+  zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, A_KC, B_KC><<<grid, 32 * NWARPS, smem, a.stream>>>(a.base, a.chain_stride, g);
   ++*a.launches;
+}
+
+// operand layouts are template parameters (a kernel that takes them at run time carries every fragment-load variant
+// in its unrolled loops: ~56 KB of code, instruction-cache misses were 20 % of the stall samples of the small products)
+template <int BM, int BN, int STAGES, int NWARPS>
+static void launch_gemm(const Arena& a, const GemmArgs& g) {
+  const bool a_kc = (g.opA == OP_N || g.opA == OP_J), b_kc = (g.opB == OP_T || g.opB == OP_C);
+  if (a_kc && b_kc) launch_gemm_l<BM, BN, STAGES, NWARPS, true, true>(a, g);
+  else if (a_kc) launch_gemm_l<BM, BN, STAGES, NWARPS, true, false>(a, g);
+  else if (b_kc) launch_gemm_l<BM, BN, STAGES, NWARPS, false, true>(a, g);
+  else launch_gemm_l<BM, BN, STAGES, NWARPS, false, false>(a, g);
 }
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
@@ -245,8 +268,9 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
     const int64_t slabs = (k + BK - 1) / BK;
     int ks = 1;
     static const bool no_auto = getenv("KBP_GEMM_NOSPLIT") != nullptr;
+    static const int warps_target = getenv("KBP_GEMM_WARPS_TARGET") ? atoi(getenv("KBP_GEMM_WARPS_TARGET")) : 900;
     if (!no_auto && warps < 600 && slabs >= 8 && tiles16 <= GEMM_MAX_TILES && a.scratch != nullptr) {
-      ks = (int)((900 + warps - 1) / warps);
+      ks = (int)((warps_target + warps - 1) / warps);
       if (ks > slabs / 4) ks = (int)(slabs / 4);
       if (ks > 16) ks = 16;
       while (ks > 1 && (int64_t)ks * m * n > a.scratch_stride) --ks;
@@ -258,7 +282,12 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
   // few dozen tiles is bound by the handful of SMs it occupies.  Pick the largest tile that still spreads over the machine.
   const int64_t ctas64 = ((n + 63) / 64) * ((m + 63) / 64) * a.nb * g.ksplit;
   const int64_t ctas32 = ((n + 31) / 32) * ((m + 31) / 32) * a.nb * g.ksplit;
-  if (g.fused) launch_gemm<16, 16, 4, 2>(a, g);
+  // tuning knobs of the small-product path (tools/gemm_bench.py sweeps them)
+  static const int fused_tile = getenv("KBP_GEMM_FUSED_TILE") ? atoi(getenv("KBP_GEMM_FUSED_TILE")) : 16;
+  static const int stages16 = getenv("KBP_GEMM_STAGES16") ? atoi(getenv("KBP_GEMM_STAGES16")) : 3;   // measured: 3 stages (30 KB, 7 CTAs per SM) beat 4 on every shape of tools/gemm_bench.py d4
+  if (g.fused && fused_tile == 32) launch_gemm<32, 32, 4, 8>(a, g);
+  else if (stages16 == 3 && (g.fused || ctas32 < 96)) launch_gemm<16, 16, 3, 2>(a, g);
+  else if (g.fused) launch_gemm<16, 16, 4, 2>(a, g);
   else if (ctas64 >= 96) launch_gemm<64, 64, 3, 8>(a, g);
   else if (ctas32 >= 96) launch_gemm<32, 32, 4, 8>(a, g);
   else launch_gemm<16, 16, 4, 2>(a, g);
@@ -269,11 +298,15 @@ static void gemm_attr() {
   constexpr int TA = (BM * LDK > BK * (BM + 2)) ? BM * LDK : BK * (BM + 2);
   constexpr int TB = (BN * LDK > BK * (BN + 2)) ? BN * LDK : BK * (BN + 2);
   constexpr size_t smem = sizeof(double2) * (size_t)STAGES * (TA + TB);
-  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 void init_gemm_attributes() {
   gemm_attr<16, 16, 4, 2>();
+  gemm_attr<16, 16, 3, 2>();
   gemm_attr<32, 32, 4, 8>();
   gemm_attr<64, 64, 3, 8>();
 }

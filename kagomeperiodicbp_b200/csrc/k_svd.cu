@@ -500,7 +500,7 @@ int svd_exact(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, i
     ++*a.launches;
   }
   // flags of the exact path live behind those of the subspace iteration (both may be in flight for different chains)
-  double* base = a.svd_off + (6 + 32 * 160) * (size_t)a.nb;
+  double* base = a.svd_off + (6 + TSVD_NPART * TSVD_PART_STRIDE) * (size_t)a.nb;
   double* prev = base;
   double* cur = base + a.nb;
   double* fro2 = base + 2 * a.nb;

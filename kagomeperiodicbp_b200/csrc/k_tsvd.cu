@@ -244,39 +244,155 @@ __device__ __forceinline__ void chol_factor(const CholWork& w, int b, int t, int
   }
 }
 
-// inverses of the 16 x 16 diagonal blocks of R (what the blocked triangular solve multiplies by), all panels in parallel:
-// thread (panel, column l) does the back substitution up column l of X = R_pp^{-1}, a 16-step dependent chain.
+// The same factorisation, unblocked and REGISTER resident (b <= 32 NC, 512 threads): the upper triangle is dealt block-cyclically,
+// thread (warp w, lane) holding the entries (i, c) with i = w + 16 r, c = lane + 32 k, so every pivot row belongs to ONE warp and
+// the active part of the matrix stays spread over all 16 warps to the end.  A step is one barrier: the owner warp publishes the
+// (unscaled) pivot row through a double-buffered shared-memory line, every thread reads the pivot, its rows' and its columns'
+// entries of that line and applies the rank-1 update to its registers (rows already factored are skipped warp-uniformly).
+// The blocked version above spends ~450 cycles per pivot step (three phases per panel, the trailing matrix through shared
+// memory); here a step is one barrier + one line read + <= 6 complex FMAs per thread.  v[r][k] is used iff r <= 2 k + 1 (the
+// other pairs lie below the diagonal for every lane; the compiler drops them).  R (upper) is left in w.S, as above.
+constexpr int CREG_LINE = 128;                                     // entries of one pivot line (b <= 128)
+
+// w.rowbuf: 4 * CREG_LINE entries (two double-buffered lines: the pivot row u_c and the multipliers a_c = conj(u_c) / pivot).
+// The loop is software pipelined: in step j the warp that owns row j + 1 updates that row FIRST and publishes it for step
+// j + 1 (pivot broadcast by shuffle -> 1 / pivot -> line stores) before it touches its other rows, so the chain
+//     barrier -> line loads -> complex FMA of the next pivot row -> shuffle -> reciprocal -> line stores -> barrier
+// is all that is serial; the other 15 warps' updates (<= 6 complex FMAs per thread) run beside it.  The update is branch-free
+// inside a row: only the register block that crosses the diagonal (k == r / 2) is predicated per lane, blocks to the right of
+// it are always inside the triangle, rows already factored are skipped per warp.  One SM's FP64 pipe (64 FMA / clk) bounds
+// the kernel from below: b^3 / 3 complex MACs = 5.5 k cycles at b = 64, ~2x that with the triangle dealt as rectangles.
+template <int NC>
+struct CholReg {
+  static constexpr int NR = 2 * NC;
+  cplx (&v)[2 * NC][NC];
+  const CholWork& w;
+  const int b, lane, wp;
+  double pd;                     // pivot of the row this warp published last
+  bool plive;
+
+  __device__ __forceinline__ CholReg(cplx (&v_)[2 * NC][NC], const CholWork& w_, int b_, int t) : v(v_), w(w_), b(b_), lane(t & 31), wp(t >> 5), pd(0.0), plive(false) {}
+
+  // row register r of this warp -= a * (pivot line), a = conj(u_i) / pivot of the warp's row i = wp + 16 r
+  __device__ __forceinline__ void update_row(int r, const cplx a, const cplx (&uc)[NC]) {
+    const int i = wp + 16 * r, kd = r >> 1;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if (k < kd) continue;
+      if (k > kd || lane + 32 * k >= i) {
+        v[r][k].x = fma(-a.x, uc[k].x, fma(a.y, uc[k].y, v[r][k].x));
+        v[r][k].y = fma(-a.x, uc[k].y, fma(-a.y, uc[k].x, v[r][k].y));
+      }
+    }
+  }
+
+  // the warp that holds pivot row jn in row register rn puts it (and the multipliers) on line jn & 1
+  __device__ __forceinline__ void publish(int rn, int jn) {
+    const int kp = rn >> 1;
+    cplx* rb = w.rowbuf + (jn & 1) * (2 * CREG_LINE);
+    cplx* ra = rb + CREG_LINE;
+    const double d = __shfl_sync(0xffffffffu, v[rn][kp].x, 16 * (rn & 1) + (jn & 15));
+    const double d0 = w.diag0[jn];
+    const bool live = d0 > 0.0 && d > TSVD_PIVOT_DEAD * d0;        // NaN -> dropped
+    const double inv = live ? 1.0 / d : 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      if (k < kp) continue;
+      rb[lane + 32 * k] = v[rn][k];
+      ra[lane + 32 * k] = cmake(v[rn][k].x * inv, -v[rn][k].y * inv);
+    }
+    pd = d;
+    plive = live;
+  }
+
+  __device__ __forceinline__ void run() {
+    cplx* S = w.S;
+    const int ld = w.ld;
+    __syncthreads();                                               // w.diag0 complete
+    if (wp == 0) publish(0, 0);
+#pragma unroll
+    for (int rj = 0; rj < NR; ++rj) {
+      const int kp = rj >> 1;
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = rj * 16 + jj;
+        if (j >= b) break;
+        const cplx* rb = w.rowbuf + (j & 1) * (2 * CREG_LINE);
+        const cplx* ra = rb + CREG_LINE;
+        __syncthreads();
+        cplx uc[NC], ai[NR];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) uc[k] = k >= kp ? rb[lane + 32 * k] : cmake(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) ai[r] = r >= rj ? ra[wp + 16 * r] : cmake(0.0, 0.0);
+        // the next pivot row first
+        const bool next_here = jj < 15 ? wp == jj + 1 : wp == 0;   // warp-uniform
+        if (j + 1 < b && next_here) {
+          if (jj < 15) {
+            update_row(rj, ai[rj], uc);
+            publish(rj, j + 1);
+          } else if (rj + 1 < NR) {
+            update_row(rj + 1 < NR ? rj + 1 : rj, ai[rj + 1 < NR ? rj + 1 : rj], uc);
+            publish(rj + 1 < NR ? rj + 1 : rj, j + 1);
+          }
+        }
+        // the other rows below the pivot (rows >= b hold zeros)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          if (r < rj) continue;
+          const bool below = r > rj || wp > jj;
+          const bool done = (jj < 15 && r == rj && wp == jj + 1) || (jj == 15 && r == rj + 1 && wp == 0);
+          if (below && !done) update_row(r, ai[r], uc);
+        }
+        if (wp == jj) {                                            // row j of R, off the critical path of the other warps
+          const double ip = plive ? rsqrt(pd) : 0.0;
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            if (k < kp) continue;
+            const int c = lane + 32 * k;
+            if (c > j && c < b) S[j * ld + c] = cscale(v[rj][k], ip);
+            else if (c == j) S[j * ld + c] = cmake(plive ? pd * ip : 0.0, 0.0);
+          }
+          if (lane == 0) { w.piv[j] = plive ? pd : -1.0; w.dinv[j] = ip; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+};
+
+template <int NC>
+__device__ __forceinline__ void chol_factor_reg(const CholWork& w, int b, int t, cplx (&v)[2 * NC][NC]) {
+  CholReg<NC> c(v, w, b, t);
+  c.run();
+}
+
+// inverses of the 16 x 16 diagonal blocks of R (what the blocked triangular solve multiplies by): X = R_pp^{-1}, one HALF WARP
+// per column l of a block (lane i = row i): back substitution from row l upwards, the entry found in step k goes to the lanes
+// above it by a shuffle, each adds its term.  16 short steps per column with all columns of all blocks in flight (the
+// one-thread-per-column version before it was a 136-term dependent chain on 64 threads: as long as the factorisation).
 // Xd: nblk x 16 x 16 (shared or global memory).
 __device__ __forceinline__ void chol_diag_inverses(const CholWork& w, int b, cplx* __restrict__ Xd, int t, int nt) {
   const cplx* S = w.S;
-  const double* dinv = w.dinv;
   const int ld = w.ld;
-  const int nblk = (b + CNB - 1) / CNB;
-  for (int e = t; e < nblk * CNB; e += nt) {
-    const int pb = e / CNB, l = e - pb * CNB;
-    const int p0 = pb * CNB, pw = (p0 + CNB < b ? CNB : b - p0);
-    cplx acc[CNB];
+  const int nblk = (b + CNB - 1) / CNB, units = nblk * CNB, per_pass = nt >> 4;
+  const int hw = t >> 4, i = t & 15;
+  for (int u0 = 0; u0 < units; u0 += per_pass) {                   // uniform trip count: every lane takes part in the shuffles
+    const int u = u0 + hw;
+    const bool valid = u < units;
+    const int pb = valid ? u >> 4 : 0, l = u & 15, p0 = pb * CNB;
+    const bool row_in = p0 + i < b;
+    const double di = row_in ? w.dinv[p0 + i] : 0.0;
+    cplx acc = cmake(0.0, 0.0), mine = cmake(0.0, 0.0);
 #pragma unroll
-    for (int i = 0; i < CNB; ++i) acc[i] = cmake(0.0, 0.0);
-    cplx* Xp = Xd + pb * CNB * CNB;
-    if (l < pw) {
-#pragma unroll
-      for (int i = CNB - 1; i >= 0; --i) {
-        if (i <= l) {
-          const cplx x = i == l ? cmake(dinv[p0 + l], 0.0) : cscale(acc[i], -dinv[p0 + i]);
-          Xp[i * CNB + l] = x;
-#pragma unroll
-          for (int i2 = 0; i2 < CNB; ++i2) {
-            if (i2 < i) acc[i2] = cfma(S[(p0 + i2) * ld + p0 + i], x, acc[i2]);
-          }
-        } else {
-          Xp[i * CNB + l] = cmake(0.0, 0.0);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < CNB; ++i) Xp[i * CNB + l] = cmake(0.0, 0.0);
+    for (int k = CNB - 1; k >= 0; --k) {
+      cplx xk = cmake(0.0, 0.0);
+      if (i == k && k <= l) xk = k == l ? cmake(di, 0.0) : cscale(acc, -di);
+      if (i == k) mine = xk;
+      xk.x = __shfl_sync(0xffffffffu, xk.x, k, 16);
+      xk.y = __shfl_sync(0xffffffffu, xk.y, k, 16);
+      if (i < k && p0 + k < b && row_in) acc = cfma(S[(p0 + i) * ld + p0 + k], xk, acc);
     }
+    if (valid) Xd[pb * CNB * CNB + i * CNB + l] = mine;
   }
 }
 
@@ -290,12 +406,67 @@ __device__ __forceinline__ double chol_min_pivot(const CholWork& w, int b, int t
   return mn;
 }
 
+// Gram matrix (sum of the split-K partials, upper triangle) straight into the registers of chol_factor_reg, then the factorisation
+template <int NC>
+__device__ __forceinline__ void chol_reg_from_partials(const CholWork& w, const cplx* __restrict__ G, int nsplit, int b, int t) {
+  constexpr int NR = 2 * NC;
+  const int lane = t & 31, wp = t >> 5;
+  const long long bb = (long long)b * b;
+  cplx v[NR][NC];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      v[r][k] = cmake(0.0, 0.0);
+      if (2 * k + 1 >= r) {
+        const int i = wp + 16 * r, c = lane + 32 * k;
+        if (i < b && c < b && c >= i) {
+          const cplx* gp = G + (long long)i * b + c;
+          cplx x = gp[0];
+          if (nsplit == 4) {
+            const cplx v1 = gp[bb], v2 = gp[2 * bb], v3 = gp[3 * bb];
+            x = cadd(cadd(x, v1), cadd(v2, v3));
+          } else {
+            for (int sp = 1; sp < nsplit; ++sp) x = cadd(x, gp[(long long)sp * bb]);
+          }
+          v[r][k] = x;
+          if (c == i) w.diag0[i] = x.x;
+        }
+      }
+    }
+  chol_factor_reg<NC>(w, b, t, v);
+}
+
+// the same from a Gram matrix already in w.S (R overwrites it)
+template <int NC>
+__device__ __forceinline__ void chol_reg_from_smem(const CholWork& w, int b, int t) {
+  constexpr int NR = 2 * NC;
+  const int lane = t & 31, wp = t >> 5;
+  cplx v[NR][NC];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      v[r][k] = cmake(0.0, 0.0);
+      if (2 * k + 1 >= r) {
+        const int i = wp + 16 * r, c = lane + 32 * k;
+        if (i < b && c < b && c >= i) {
+          v[r][k] = w.S[i * w.ld + c];
+          if (c == i) w.diag0[i] = v[r][k].x;
+        }
+      }
+    }
+  chol_factor_reg<NC>(w, b, t, v);
+}
+
+constexpr int CREG_BMAX = 96;             // widest matrix of the register-resident factorisation (NC = 3: 12 entries per thread)
+
 __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
                                                     long long Dinv_, long long Xd_, int b, double* __restrict__ stat, const int* __restrict__ mask,
                                                     int mask_want) {
   if (mask && mask[blockIdx.x] != mask_want) return;
   extern __shared__ __align__(16) unsigned char ch_raw[];
-  __shared__ cplx rowbuf[4 * CNB];
+  __shared__ cplx rowbuf[4 * CREG_LINE];
   CholWork w;
   w.ld = b + 1;                                                    // odd row stride: the 16 rows of a panel fall into different banks
   w.S = reinterpret_cast<cplx*>(ch_raw);
@@ -308,7 +479,10 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
   const cplx* G = cb + G_;
   const int t = threadIdx.x, nt = blockDim.x;
-  {
+  if (b <= 32) chol_reg_from_partials<1>(w, G, nsplit, b, t);
+  else if (b <= 64) chol_reg_from_partials<2>(w, G, nsplit, b, t);
+  else if (b <= CREG_BMAX) chol_reg_from_partials<3>(w, G, nsplit, b, t);
+  else {
     // sum of the split-K partial Gram matrices; (row, column) from the warp / lane, no integer division, all partials of
     // several rows in flight at once
     const int lane = t & 31, wp = t >> 5, nw = nt >> 5;
@@ -326,11 +500,11 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
         S[r * ld + c] = v;
       }
     }
+    __syncthreads();
+    for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
+    __syncthreads();
+    chol_factor(w, b, t, nt);
   }
-  __syncthreads();
-  for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
-  __syncthreads();
-  chol_factor(w, b, t, nt);
   cplx* R = cb + R_;
   for (int r = t >> 5; r < b; r += nt >> 5)
     for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
@@ -368,7 +542,7 @@ __global__ void __launch_bounds__(512) cholqr_cluster_kernel(cplx* __restrict__ 
   cgx::cluster_group cluster = cgx::this_cluster();
   const int rank = (int)cluster.block_rank(), C = (int)cluster.num_blocks();
   extern __shared__ __align__(16) unsigned char cq_raw[];
-  __shared__ cplx rowbuf[4 * CNB];
+  __shared__ cplx rowbuf[4 * CREG_LINE];
   const int b = g.b, ld = b + 1, rl = g.rl, nblk = (b + CNB - 1) / CNB;
   CholWork w;
   w.ld = ld;
@@ -445,10 +619,15 @@ __global__ void __launch_bounds__(512) cholqr_cluster_kernel(cplx* __restrict__ 
   } else {
     __syncthreads();
   }
-  for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
-  __syncthreads();
   // ---- 3. Cholesky (redundant per CTA)
-  chol_factor(w, b, t, nt);
+  if (b <= 32) chol_reg_from_smem<1>(w, b, t);
+  else if (b <= 64) chol_reg_from_smem<2>(w, b, t);
+  else if (b <= CREG_BMAX) chol_reg_from_smem<3>(w, b, t);
+  else {
+    for (int i = t; i < b; i += nt) w.diag0[i] = S[i * ld + i].x;
+    __syncthreads();
+    chol_factor(w, b, t, nt);
+  }
   if (rank == 0) {
     if (g.R >= 0) {
       cplx* R = cb + g.R;
@@ -518,7 +697,7 @@ static int cholqr_cluster_rl(int64_t rows, int b) {
   if (!on) return 0;
   for (int rl = 64; rl >= 32; rl >>= 1) {
     if ((rows + rl - 1) / rl > 8) continue;
-    if (cholqr_cluster_smem(b, rl) > 225 * 1024) continue;
+    if (cholqr_cluster_smem(b, rl) > 217 * 1024) continue;
     // the all-reduce keeps at most 4 entries per thread in registers
     const int C = (int)((rows + rl - 1) / rl);
     if (((int64_t)b * (b + 1) + C - 1) / C > 4 * 512) continue;
@@ -529,17 +708,22 @@ static int cholqr_cluster_rl(int64_t rows, int b) {
 
 // Out (rows x b) = Y R^{-1} for upper-triangular R by block forward substitution over the 16-column panels:
 //     x_p = (y_p - sum_{r < p} x_r R_{r,p}) X_pp,        X_pp = inverse of the diagonal block (from chol_kernel).
-// One CTA per 32 rows, thread (row, c): the 16 threads of a row sit in one half warp, so the panel loop needs warp-level
-// synchronisation only.  The X_pp and the solved entries live in shared memory, R is read through L2.
+// One CTA per TRSM_ROWS rows, ONE WARP PER ROW: lane = (h, c), c = column inside the panel, h = which half of the two inner
+// sums (over the solved entries, over the rows of X_pp) the lane adds up; the halves meet in one shuffle.  The kernel is a
+// chain of dependent instructions per warp (~12 cycles each), so what counts is how few of them a warp executes: with one
+// row per half warp and undivided sums the 64-column solve took ~1900 instructions per warp (15 us).
+// The X_pp, the blocks of R above the diagonal and the solved entries live in shared memory.
+constexpr int TRSM_ROWS = 16;
+
 __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
                                                    long long Out_, int rows, int b, const int* __restrict__ mask, int mask_want) {
   if (mask && mask[blockIdx.y] != mask_want) return;
   extern __shared__ __align__(16) unsigned char tr_raw[];
   const int nblk = (b + CNB - 1) / CNB;
   cplx* Xs = reinterpret_cast<cplx*>(tr_raw);                     // nblk x 16 x 16: inverses of the diagonal blocks
-  cplx* xs = Xs + (size_t)nblk * CNB * CNB;                       // 32 x (b + 1): solved entries of the CTA's rows
-  cplx* tmp = xs + 32 * (size_t)(b + 1);                          // 32 x 17
-  cplx* Rs = tmp + 32 * 17;                                       // the blocks of R above the diagonal blocks, packed per block column
+  cplx* xs = Xs + (size_t)nblk * CNB * CNB;                       // TRSM_ROWS x (16 nblk + 1): solved entries of the CTA's rows
+  cplx* tmp = xs + TRSM_ROWS * (size_t)(nblk * CNB + 1);          // TRSM_ROWS x 17
+  cplx* Rs = tmp + TRSM_ROWS * 17;                                // the blocks of R above the diagonal blocks, packed per block column
   cplx* cb = base + (long long)blockIdx.y * chain_stride;
   const cplx* R = cb + R_;
   const cplx* Xd = cb + Xd_;
@@ -547,45 +731,69 @@ __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long
   for (int e = t; e < nblk * CNB * CNB; e += blockDim.x) Xs[e] = Xd[e];
   // R is shared by every row: one coalesced pass through L2 instead of a dependent L2 load per inner-loop step
   // (block column pb holds rows [0, 16 pb) x columns [16 pb, 16 pb + 16) at offset 256 pb (pb - 1) / 2)
-  {
-    const int total = CNB * CNB * (nblk * (nblk - 1) / 2);
-    for (int e = t; e < total; e += blockDim.x) {
-      int pb = 1, off = 0;
-      while (e >= off + CNB * CNB * pb) { off += CNB * CNB * pb; ++pb; }
-      const int loc = e - off, i = loc >> 4, c = loc & 15, col = pb * CNB + c;
-      Rs[e] = col < b ? __ldg(R + (long long)i * b + col) : cmake(0.0, 0.0);
+  for (int pb = 1; pb < nblk; ++pb) {
+    cplx* dst = Rs + CNB * CNB * (pb * (pb - 1) / 2);
+    for (int e = t; e < CNB * CNB * pb; e += blockDim.x) {
+      const int i = e >> 4, col = pb * CNB + (e & 15);
+      dst[e] = col < b ? __ldg(R + (long long)i * b + col) : cmake(0.0, 0.0);
     }
   }
-  __syncthreads();
-  const int r = t >> 4, c = t & 15;
-  const int row = blockIdx.x * 32 + r;
+  const int r = t >> 5, lane = t & 31, c = lane & 15, h = lane >> 4;
+  const int row = blockIdx.x * TRSM_ROWS + r;
   const bool ok = row < rows;
   const cplx* y = cb + Y_ + (long long)row * b;
   cplx* out = cb + Out_ + (long long)row * b;
-  cplx* xr = xs + r * (b + 1);
+  cplx* xr = xs + r * (nblk * CNB + 1);
   cplx* tr = tmp + r * 17;
+  // the row's entries, one per lane and pair of panels: issued before the barrier so their latency hides behind the staging
+  cplx yv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int col = (2 * u + h) * CNB + c;
+    yv[u] = (ok && col < b) ? y[col] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
   for (int pb = 0; pb < nblk; ++pb) {
     const int p0 = pb * CNB, col = p0 + c;
-    cplx acc = (ok && col < b) ? y[col] : cmake(0.0, 0.0);
+    // y[col] sits in lane (pb & 1, c), register pb >> 1 (panels >= 8: straight from memory)
+    cplx acc;
+    {
+      const int u = pb >> 1;
+      cplx mine = u == 0 ? yv[0] : u == 1 ? yv[1] : u == 2 ? yv[2] : u == 3 ? yv[3] : ((ok && col < b && h == (pb & 1)) ? y[col] : cmake(0.0, 0.0));
+      if (h != (pb & 1)) mine = cmake(0.0, 0.0);
+      acc = mine;                                                  // the half that does not hold y starts from zero
+    }
     {
       const cplx* rc = Rs + CNB * CNB * (pb * (pb - 1) / 2) + c;  // column c of block column pb
-      cplx acc2 = cmake(0.0, 0.0);
-      int i = 0;
-      for (; i + 1 < p0; i += 2) {                                 // two independent chains
+      const int half = p0 >> 1, i0 = h * half, i1 = i0 + half;    // p0 is a multiple of 16: both halves have a multiple of 8 terms
+      cplx a1 = cmake(0.0, 0.0), a2 = a1, a3 = a1;
+      for (int i = i0; i < i1; i += 4) {                           // four independent chains
         const cplx v0 = cmul(xr[i], rc[i * CNB]), v1 = cmul(xr[i + 1], rc[(i + 1) * CNB]);
+        const cplx v2 = cmul(xr[i + 2], rc[(i + 2) * CNB]), v3 = cmul(xr[i + 3], rc[(i + 3) * CNB]);
         acc.x -= v0.x; acc.y -= v0.y;
-        acc2.x -= v1.x; acc2.y -= v1.y;
+        a1.x -= v1.x; a1.y -= v1.y;
+        a2.x -= v2.x; a2.y -= v2.y;
+        a3.x -= v3.x; a3.y -= v3.y;
       }
-      acc.x += acc2.x; acc.y += acc2.y;
+      acc.x += (a1.x + a2.x) + a3.x; acc.y += (a1.y + a2.y) + a3.y;
     }
-    tr[c] = acc;
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    if (h == 0) tr[c] = acc;
     __syncwarp();
-    cplx x = cmake(0.0, 0.0);
-    const cplx* X = Xs + pb * CNB * CNB;
+    // x[c] = sum_{cp <= c} tr[cp] X[cp][c]: half h adds the rows cp in [8 h, 8 h + 8)
+    cplx x = cmake(0.0, 0.0), x2 = x;
+    const cplx* X = Xs + pb * CNB * CNB + (h * 8) * CNB + c;
+    const cplx* trh = tr + h * 8;
 #pragma unroll
-    for (int cp = 0; cp < CNB; ++cp)
-      if (cp <= c) x = cfma(tr[cp], X[cp * CNB + c], x);
-    if (col < b) {
+    for (int cp = 0; cp < 8; cp += 2) {
+      if (h * 8 + cp <= c) x = cfma(trh[cp], X[cp * CNB], x);
+      if (h * 8 + cp + 1 <= c) x2 = cfma(trh[cp + 1], X[(cp + 1) * CNB], x2);
+    }
+    x.x += x2.x; x.y += x2.y;
+    x.x += __shfl_xor_sync(0xffffffffu, x.x, 16);
+    x.y += __shfl_xor_sync(0xffffffffu, x.y, 16);
+    if (h == 0 && col < b) {
       xr[col] = x;
       if (ok) out[col] = x;
     }
@@ -600,8 +808,8 @@ __global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long
 // Only the part of the residual OUTSIDE span(Vh) counts (C - T Vh): the part inside is a change of gauge of the kept
 // bond, and it is also where the rounding of US = A Vh^H (absolute error eps s_1, amplified by A^H to eps s_1^2) lands,
 // which would otherwise put a floor of eps s_1 / s_j under the test.
-constexpr int NPART = 32;
-constexpr int PART_STRIDE = 160;     // doubles per (chain, part): keep <= 128 row sums + 2 norms
+constexpr int NPART = TSVD_NPART;              // enough CTAs to pull A and P (m x n each) through L2 at its bandwidth, not at one SM's latency
+constexpr int PART_STRIDE = TSVD_PART_STRIDE;  // doubles per (chain, part): keep <= 128 row sums + 2 norms
 
 __global__ void __launch_bounds__(256) tsvd_check1_kernel(const cplx* __restrict__ base, long long chain_stride, long long C_, long long TV_,
                                                           long long A_, long long P_, int m, int n, int keep, double* __restrict__ part,
@@ -680,20 +888,21 @@ __global__ void __launch_bounds__(128) tsvd_check2_kernel(const cplx* __restrict
   }
 }
 
-// One CTA per chain: scale US by 1 / ||A||_F (nr_bulk) and update the slots from the norms check2 left behind.
-__global__ void __launch_bounds__(1024) tsvd_finalize_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots, int n_slots,
-                                                             long long US_, long long mk, int nr_bulk, int slot_lognorm, int slot_trunc,
-                                                             const double* __restrict__ norms, const int* __restrict__ mask, int mask_want) {
-  if (mask && mask[blockIdx.x] != mask_want) return;
-  cplx* US = base + (long long)blockIdx.x * chain_stride + US_;
-  const double fro2 = norms[2 * blockIdx.x], disc = norms[2 * blockIdx.x + 1];
+// grid (FIN_CTAS, nb): scale US by 1 / ||A||_F (nr_bulk); CTA 0 of a chain updates the slots from the norms check2 left behind.
+constexpr int FIN_CTAS = 8;
+__global__ void __launch_bounds__(256) tsvd_finalize_kernel(cplx* __restrict__ base, long long chain_stride, double* __restrict__ slots, int n_slots,
+                                                            long long US_, long long mk, int nr_bulk, int slot_lognorm, int slot_trunc,
+                                                            const double* __restrict__ norms, const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.y] != mask_want) return;
+  cplx* US = base + (long long)blockIdx.y * chain_stride + US_;
+  const double fro2 = norms[2 * blockIdx.y], disc = norms[2 * blockIdx.y + 1];
   const double frob = sqrt(fro2);
   if (nr_bulk && frob > 0.0) {
     const double sc = 1.0 / frob;
-    for (long long e = threadIdx.x; e < mk; e += blockDim.x) US[e] = cscale(US[e], sc);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < mk; e += (long long)gridDim.x * blockDim.x) US[e] = cscale(US[e], sc);
   }
-  if (threadIdx.x == 0) {
-    double* sl = slots + (long long)blockIdx.x * n_slots;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double* sl = slots + (long long)blockIdx.y * n_slots;
     if (nr_bulk && slot_lognorm >= 0 && frob > 0.0) sl[slot_lognorm] += log(frob);
     if (slot_trunc >= 0 && fro2 > 0.0) sl[slot_trunc] += sqrt(disc / fro2);
   }
@@ -828,9 +1037,10 @@ static int64_t cholqr_pass_narrow(const Arena& a, int64_t Y, int64_t T, int64_t 
   PM(2);
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
-    const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + 32 * (size_t)(b + 1) + 32 * 17 +
+    const size_t smem2 = sizeof(double2) * ((size_t)nblk * CNB * CNB + TRSM_ROWS * (size_t)(nblk * CNB + 1) + TRSM_ROWS * 17 +
                                             (size_t)CNB * CNB * (nblk * (nblk - 1) / 2)) + 32;
-    trsm_kernel<<<dim3((unsigned)((rows + 31) / 32), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b, a.mask, a.mask_want);
+    trsm_kernel<<<dim3((unsigned)((rows + TRSM_ROWS - 1) / TRSM_ROWS), a.nb), 512, smem2, a.stream>>>(a.base, a.chain_stride, Y, R_out, Xd, T, (int)rows, b, a.mask,
+                                                                                                      a.mask_want);
     ++*a.launches;
     PM(3);
   }
@@ -1150,8 +1360,8 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
     }
   }
   // ---- accepted chains: scale US, update the slots
-  tsvd_finalize_kernel<<<a.nb, 1024, 0, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, US, m * keep, nr_bulk, slot_lognorm, slot_trunc, norms,
-                                                     a.chain_state, CHAIN_ACCEPTED);
+  tsvd_finalize_kernel<<<dim3(FIN_CTAS, a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, a.slots, a.n_slots, US, m * keep, nr_bulk, slot_lognorm, slot_trunc,
+                                                                    norms, a.chain_state, CHAIN_ACCEPTED);
   ++*a.launches;
   // ---- chains the iteration could not settle: exact block-Jacobi SVD of the same matrix
   if (a.capture) {
@@ -1171,8 +1381,8 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
 }
 
 void init_tsvd_attributes() {
-  cudaFuncSetAttribute(cholqr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);   // + static shared memory <= 227 KB
-  cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  cudaFuncSetAttribute(cholqr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);   // + 8 KB static shared memory <= 227 KB
+  cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);
   cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
 }
 

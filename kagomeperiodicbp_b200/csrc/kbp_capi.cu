@@ -166,7 +166,7 @@ int kbp_reserve(kbp_ctx* c, int64_t chain_elems, int nb, int n_slots) {
     CU(c, cudaMalloc(&c->scratch, sizeof(double2) * (size_t)KBP_GEMM_SCRATCH * nb));
     CU(c, cudaMalloc(&c->counters_dev, sizeof(int) * (size_t)4096 * nb));
     CU(c, cudaMemsetAsync(c->counters_dev, 0, sizeof(int) * (size_t)4096 * nb, c->stream));
-    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)(6 + 32 * 160 + 3) * nb));
+    CU(c, cudaMalloc(&c->svd_off, sizeof(double) * (size_t)kbp::SVD_OFF_DOUBLES_PER_CHAIN * nb));
     CU(c, cudaMallocHost(&c->svd_off_host, sizeof(double) * 4 * nb));
     CU(c, cudaMalloc(&c->ctl, sizeof(kbp::SvdCtl) + sizeof(int) * (size_t)nb));
     CU(c, cudaMemsetAsync(c->ctl, 0, sizeof(kbp::SvdCtl) + sizeof(int) * (size_t)nb, c->stream));

@@ -28,6 +28,12 @@ struct SvdCtl {
 };
 enum { CHAIN_RUNNING = 0, CHAIN_ACCEPTED = 1, CHAIN_EXACT = 2 };
 
+// partial sums of the subspace-SVD check kernels: [nb][TSVD_NPART][TSVD_PART_STRIDE] doubles behind the 6 per-chain scalars
+// of Arena::svd_off (TSVD_PART_STRIDE: keep <= 128 row sums + 2 norms); 3 more doubles per chain follow (block-Jacobi flags)
+constexpr int TSVD_NPART = 128;
+constexpr int TSVD_PART_STRIDE = 160;
+constexpr int SVD_OFF_DOUBLES_PER_CHAIN = 6 + TSVD_NPART * TSVD_PART_STRIDE + 3;
+
 struct Arena {
   double2* base;          // nb * chain_stride complex128 elements
   int64_t chain_stride;   // elements per chain

@@ -150,12 +150,20 @@ static bool qr_tsqr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t wor
   return false;
 }
 
-void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
-  if (m == 0 || n == 0) return;
+// the unconditionally stable path: Householder
+void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   if (qr_cluster(a, A, Q, R, m, n)) return;                // shared-memory resident, rows over a cluster (k_qr_cluster.cu)
   if (qr_tsqr(a, A, Q, R, work, m, n)) return;
   qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n);
   ++*a.launches;
+}
+
+bool qr_cholqr2(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);   // k_tsvd.cu
+
+void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
+  if (m == 0 || n == 0) return;
+  if (qr_cholqr2(a, A, Q, R, work, m, n)) return;          // tall and skinny: Cholesky-QR twice, Householder only if the Gram matrix is too ill conditioned
+  qr_householder(a, A, Q, R, work, m, n);
 }
 
 }  // namespace kbp

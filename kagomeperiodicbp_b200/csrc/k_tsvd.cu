@@ -1084,6 +1084,38 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Thin QR of a TALL matrix (m >= 4 n, 8 <= n <= 96) as Cholesky-QR twice:  A = Q1 R1,  Q1 = Q R2,  R = R2 R1  -- three
+// launches per pass (split-K Gram product on the DMMA pipe, register Cholesky, triangular solve) instead of a Householder
+// sweep whose every column costs two exchanges over distributed shared memory (512 x 32: ~190 us against ~60 us).
+// Cholesky-QR squares the condition number, so it is used only where that is harmless: the pivots are invariant under
+// column scaling, and the smallest pivot / diagonal of pass 1 bounds 1 / cond^2 of the column-scaled matrix.  With a ratio
+// >= CHOLQR2_MIN_PIVOT the first pass leaves ||Q1^H Q1 - I|| <~ eps / ratio <= 1e-5 and the second pass brings it to eps.
+// Anything else -- smaller pivots, numerically dependent (dropped) columns, non-finite entries -- is decided ON THE DEVICE and
+// sends the whole op to the Householder kernels (IF node of the program's graph; host-driven mode reads the flag back).
+// The boundary-MPS sites of a converged BP run have scaled condition numbers of 1e2 .. 1e6 (measured on the op streams of
+// the CPU tier); the rank-deficient sites of the first iterations from product messages take the fallback.
+constexpr double CHOLQR2_MIN_PIVOT = 1e-11;
+
+__global__ void cholqr2_decide_kernel(SvdCtl* __restrict__ ctl, const double* __restrict__ stat, const cplx* __restrict__ base, long long chain_stride,
+                                      long long R1_, long long R2_, int n, int nb, cudaGraphConditionalHandle h_if, int use_handles) {
+  // one warp: lanes over the diagonal entries
+  int bad = 0;
+  for (int c = 0; c < nb; ++c) {
+    const double pv = stat[c];
+    if (!(pv >= CHOLQR2_MIN_PIVOT)) bad = 1;                       // also NaN
+    const cplx* R1 = base + (long long)c * chain_stride + R1_;
+    const cplx* R2 = base + (long long)c * chain_stride + R2_;
+    for (int j = threadIdx.x; j < n; j += 32)
+      if (!(R1[(long long)j * n + j].x > 0.0) || !(R2[(long long)j * n + j].x > 0.0)) bad = 1;     // dropped column
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (threadIdx.x == 0) {
+    ctl->any_exact = bad;
+    if (use_handles) cudaGraphSetConditional(h_if, bad ? 1u : 0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The decision after every Rayleigh-Ritz round, on the device (one thread): per chain accept / iterate further / exact path.
 // A chain that is done leaves the RUNNING state, which is the per-chain predicate of every launch of the following rounds.
 //   accept    residual <= TSVD_RES_TOL, Cholesky pivots of the round trustworthy, no collapse of the kept spectrum
@@ -1378,6 +1410,39 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   }
   if (!a.capture && a.tsvd_rounds) (*a.tsvd_rounds)[a.op_key] = rounds;
   return rounds;
+}
+
+void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);   // k_qr.cu
+
+bool qr_cholqr2(const Arena& a0, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
+  static const bool on = !(getenv("KBP_QR_CHOLQR2") && atoi(getenv("KBP_QR_CHOLQR2")) == 0);
+  if (!on || n < 8 || n > CREG_BMAX || m < 4 * n) return false;
+  const int b = (int)n, nblk = (b + CNB - 1) / CNB;
+  const int64_t bb = n * n, need = m * n + GRAM_SPLIT * bb + 2 * bb + n + (int64_t)nblk * CNB * CNB + 8;
+  const int64_t k = n;
+  if (need > m * n + m * k + k + 8) return false;                  // the op's workspace (kbp_qr_work_elems)
+  Arena a = a0;
+  a.mask = nullptr;
+  const int64_t T1 = work, Gp = T1 + m * n, R1 = Gp + GRAM_SPLIT * bb, R2 = R1 + bb, Dinv = R2 + bb;
+  double* stat = a.svd_off;
+  tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
+  ++*a.launches;
+  cholqr_pass_narrow(a, A, T1, Gp, Dinv, R1, m, b, stat);          // A = Q1 R1
+  cholqr_pass_narrow(a, T1, Q, Gp, Dinv, R2, m, b, stat);          // Q1 = Q R2
+  gemm(a, R, R2, R1, n, n, n, OP_N, OP_N);                         // R = R2 R1 (upper triangular)
+  const cudaGraphConditionalHandle h_if = new_cond_handle(a);
+  cholqr2_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, stat, a.base, a.chain_stride, R1, R2, b, a.nb, h_if, a.capture ? 1 : 0);
+  ++*a.launches;
+  if (a.capture) {
+    Arena body;
+    if (!begin_cond_body(a, h_if, false, &body)) { qr_householder(a, A, Q, R, work, m, n); return true; }   // cannot nest deeper: stable path unconditionally
+    qr_householder(body, A, Q, R, work, m, n);
+    end_body(body);
+  } else {
+    if (read_ctl(a) != cudaSuccess) return true;
+    if (a.ctl_host->any_exact) qr_householder(a, A, Q, R, work, m, n);
+  }
+  return true;
 }
 
 void init_tsvd_attributes() {

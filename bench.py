@@ -312,6 +312,7 @@ class SideSet:
         self.comps = {s: bp.compile_side_program(N, 2, D, s, chi, shapes, damping if damping else None) for s in self.sides}
         self.engs = {s: get_engine((key, s), dev) for s in self.sides}
         self.h2d = self.d2h = 0
+        self.respec = 0
         for s in self.sides:
             batch = [bp._side_inputs(c, m, self.comps[s]) for c, m in zip(cells, msgs_list)]
             self.comps[s].load(self.engs[s], self.B)
@@ -325,7 +326,11 @@ class SideSet:
 
     def step(self):
         bp = self.bp
-        if self.ready():
+        if self.ready() and max(len(self.comps[s].words) for s in self.sides) > bp.BIG_GRAPH_WORDS:
+            futs = [bp._pool.submit(self.comps[s].run_resident, self.engs[s], (bp.E_SVD_NOCONV,)) for s in self.sides]   # big graphs: the launch
+            for f in futs:                                         # call itself takes 20-30 ms of host time each (belief_propagation.py)
+                f.result()
+        elif self.ready():
             for s in self.sides:                                   # six graph launches from this thread
                 self.comps[s].run_resident(self.engs[s], (bp.E_SVD_NOCONV,))
         else:                                                      # first sight: host-driven loops, one thread per side
@@ -334,6 +339,15 @@ class SideSet:
                 f.result()
         for s in self.sides:
             self.engs[s].sync()
+        for s in self.sides:                                       # speculative-graph protocol (include/kbp.h): part of the step
+            self.respec += bool(self.comps[s].verify_resident(self.engs[s], (bp.E_SVD_NOCONV,)))
+
+    def spec_counters(self):
+        out = {"host_driven_reruns": self.respec}
+        for s in self.sides:
+            for k, v in self.engs[s].spec_counters().items():
+                out[k] = out.get(k, 0) + v
+        return out
 
     def launches(self):
         return sum(self.engs[s].launch_count() for s in self.sides)
@@ -511,6 +525,7 @@ def main():
             tj = json.load(open(tf))
             traffic, traffic_src = tj.get("dominant_kernel_dram_bytes_per_launch"), tj.get("source")
         paths = ss.svd_counters()
+        paths.update(ss.spec_counters())
         line["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                             "traffic": traffic, "traffic_source": traffic_src,
                             "kernel": "whole BP iteration; dominant family = truncated SVD by subspace iteration (zgemm_dmma_kernel + chol_kernel + "

@@ -309,7 +309,13 @@ def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device
     if all(eng.graph_ready(comp.words) for _, comp, _, eng in todo):
         # steady state: every side program is one CUDA-graph launch on its own stream -- queue all of them from this thread,
         # then collect; the host takes no part in the iteration and no launch thread spins on a stream
-        rcs = [comp.launch(eng, batch, soft_errors=(E_SVD_NOCONV,)) for _, comp, batch, eng in todo]
+        if max(len(comp.words) for _, comp, _, _ in todo) > BIG_GRAPH_WORDS:
+            # the launch call of a very large graph (N = 6: ~23k kernel nodes) keeps the host busy for 20-30 ms: six short-lived
+            # launch threads (they return as soon as the graph is queued) start the sides together instead of 150 ms apart
+            futs = [_pool.submit(comp.launch, eng, batch, (E_SVD_NOCONV,)) for _, comp, batch, eng in todo]
+            rcs = [f.result() for f in futs]
+        else:
+            rcs = [comp.launch(eng, batch, soft_errors=(E_SVD_NOCONV,)) for _, comp, batch, eng in todo]
         for (side, comp, batch, eng), rc in zip(todo, rcs):
             res[side] = comp.collect(eng, len(batch), rc)
         return res
@@ -319,6 +325,9 @@ def run_sides(N: int, cells: list, messages_list: list, config: BPConfig, device
         side, outs, slots, rc = f.result()
         res[side] = (outs, slots, rc)
     return res
+
+
+BIG_GRAPH_WORDS = 20000      # op-stream length from which a program's graph launch is worth its own host thread
 
 
 def assemble_step(res: dict, n_cells: int, config: BPConfig):

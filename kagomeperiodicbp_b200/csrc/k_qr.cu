@@ -9,7 +9,9 @@
 namespace kbp {
 
 __global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ base, long long chain_stride, long long A_,
-                                                             long long Q_, long long R_, long long work_, int m, int n) {
+                                                             long long Q_, long long R_, long long work_, int m, int n,
+                                                             const int* __restrict__ mask, int mask_want) {
+  if (mask && mask[blockIdx.x] != mask_want) return;
   __shared__ double red[34];
   __shared__ cplx sh_inv_u0, sh_s;
   __shared__ double sh_tau;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(512) qr_householder_kernel(cplx* __restrict__ 
 }
 
 bool qr_cluster_fits(int64_t m, int64_t n);
+void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);
 
 // Tall matrices the cluster kernel does not take (1024 x 64 at D = 4, 2592 x 72 at D = 6): TSQR.  The rows are cut into
 // nbk blocks that it does take, A_i = Q_i R_i; the stacked R_i (nbk n x n) are factored again, [R_1; ...; R_nbk] = Qs R; then
@@ -140,7 +143,7 @@ static bool qr_tsqr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t wor
       const int64_t rows = i + 1 < nbk ? mb : last;
       if (!qr_cluster(a, A + i * mb * n, T + i * mb * n, S + i * n * n, rows, n)) return false;   // (nothing launched yet if i == 0)
     }
-    qr(a, S, Qs, R, W2, nbk * n, n);
+    qr_householder(a, S, Qs, R, W2, nbk * n, n);
     for (int i = 0; i < nbk; ++i) {
       const int64_t rows = i + 1 < nbk ? mb : last;
       gemm(a, Q + i * mb * n, T + i * mb * n, Qs + i * n * n, rows, n, n, OP_N, OP_N);
@@ -154,7 +157,7 @@ static bool qr_tsqr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t wor
 void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   if (qr_cluster(a, A, Q, R, m, n)) return;                // shared-memory resident, rows over a cluster (k_qr_cluster.cu)
   if (qr_tsqr(a, A, Q, R, work, m, n)) return;
-  qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n);
+  qr_householder_kernel<<<a.nb, 512, 0, a.stream>>>(a.base, a.chain_stride, A, Q, R, work, (int)m, (int)n, a.mask, a.mask_want);
   ++*a.launches;
 }
 

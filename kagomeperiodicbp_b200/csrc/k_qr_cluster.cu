@@ -31,7 +31,7 @@ constexpr size_t QRC_SMEM_MAX = 220 * 1024;
 constexpr double QRC_BIG = 2.582249878086908589655919172e120;        // 2^400
 constexpr double QRC_TINY2 = 1e-200;                                 // below this a plain sum of squares is not trusted
 
-struct QrcArgs { long long A, Q, R; int m, n; };
+struct QrcArgs { long long A, Q, R; int m, n; const int* mask; int mask_want; };   // mask: per-chain predicate (kbp_ops.cuh: Arena::mask)
 
 __device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t to_rank(uint32_t addr, uint32_t rank) {
@@ -95,6 +95,7 @@ __device__ __forceinline__ cplx half_sum(cplx v) {
 }
 
 __global__ void __launch_bounds__(QRC_THREADS) qr_cluster_kernel(cplx* __restrict__ base, long long chain_stride, QrcArgs g) {
+  if (g.mask && g.mask[blockIdx.y] != g.mask_want) return;           // the whole cluster of a chain leaves together
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -279,7 +280,7 @@ bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int6
   while (C <= 8 && ((m + C - 1) / C > QRC_MLOC_MAX || qrc_smem((int)m, (int)n, C) > QRC_SMEM_MAX)) C <<= 1;
   if (C > 8) return false;
   QrcArgs g;
-  g.A = A; g.Q = Q; g.R = R; g.m = (int)m; g.n = (int)n;
+  g.A = A; g.Q = Q; g.R = R; g.m = (int)m; g.n = (int)n; g.mask = a.mask; g.mask_want = a.mask_want;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)C, (unsigned)a.nb);
   cfg.blockDim = dim3(QRC_THREADS);

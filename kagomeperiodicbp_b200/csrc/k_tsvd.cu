@@ -461,28 +461,67 @@ __device__ __forceinline__ void chol_reg_from_smem(const CholWork& w, int b, int
 
 constexpr int CREG_BMAX = 96;             // widest matrix of the register-resident factorisation (NC = 3: 12 entries per thread)
 
-__global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long long chain_stride, long long G_, int nsplit, long long R_,
-                                                    long long Dinv_, long long Xd_, int b, double* __restrict__ stat, const int* __restrict__ mask,
-                                                    int mask_want) {
-  if (mask && mask[blockIdx.x] != mask_want) return;
-  extern __shared__ __align__(16) unsigned char ch_raw[];
-  __shared__ cplx rowbuf[4 * CREG_LINE];
+// One kernel per register-block count NC (and one for the blocked fallback), so that each gets its own register
+// allocation: NC <= 2 (b <= 64: every truncation at D <= 4) fits 64 registers per thread, i.e. HALF an SM's register file.
+// The single kernel before it took 128 x 512 = the whole file: its CTA could only start on an SM with nothing else on it,
+// and with several program graphs in flight (six block sides) it queued behind the other chains' GEMM CTAs.
+struct CholArgs {
+  long long G, R, Dinv, Xd;
+  int nsplit, b;
+  const int* mask;
+  int mask_want;
+};
+
+__device__ __forceinline__ void chol_kernel_tail(const CholWork& w, cplx* cb, const CholArgs& g, double* __restrict__ stat, int t, int nt) {
+  const int b = g.b, ld = w.ld;
+  const cplx* S = w.S;
+  cplx* R = cb + g.R;
+  for (int r = t >> 5; r < b; r += nt >> 5)
+    for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
+  cplx* Dv = cb + g.Dinv;
+  for (int i = t; i < b; i += nt) Dv[i] = cmake(w.dinv[i], 0.0);
+  chol_diag_inverses(w, b, cb + g.Xd, t, nt);
+  if (t < 32) {
+    const double mn = chol_min_pivot(w, b, t);
+    if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], mn);
+  }
+}
+
+__device__ __forceinline__ CholWork chol_work(unsigned char* raw, cplx* rowbuf, int b) {
   CholWork w;
   w.ld = b + 1;                                                    // odd row stride: the 16 rows of a panel fall into different banks
-  w.S = reinterpret_cast<cplx*>(ch_raw);
+  w.S = reinterpret_cast<cplx*>(raw);
   w.diag0 = reinterpret_cast<double*>(w.S + (size_t)b * w.ld);
   w.dinv = w.diag0 + b;
   w.piv = w.dinv + b;
   w.rowbuf = rowbuf;
+  return w;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(512, NC <= 2 ? 2 : 1) chol_reg_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
+  if (g.mask && g.mask[blockIdx.x] != g.mask_want) return;
+  extern __shared__ __align__(16) unsigned char ch_raw[];
+  __shared__ cplx rowbuf[4 * CREG_LINE];
+  const CholWork w = chol_work(ch_raw, rowbuf, g.b);
+  cplx* cb = base + (long long)blockIdx.x * chain_stride;
+  const int t = threadIdx.x;
+  chol_reg_from_partials<NC>(w, cb + g.G, g.nsplit, g.b, t);
+  chol_kernel_tail(w, cb, g, stat, t, blockDim.x);
+}
+
+__global__ void __launch_bounds__(512) chol_blocked_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
+  if (g.mask && g.mask[blockIdx.x] != g.mask_want) return;
+  extern __shared__ __align__(16) unsigned char ch_raw[];
+  __shared__ cplx rowbuf[4 * CNB];
+  const int b = g.b, nsplit = g.nsplit;
+  const CholWork w = chol_work(ch_raw, rowbuf, b);
   cplx* S = w.S;
   const int ld = w.ld;
   cplx* cb = base + (long long)blockIdx.x * chain_stride;
-  const cplx* G = cb + G_;
+  const cplx* G = cb + g.G;
   const int t = threadIdx.x, nt = blockDim.x;
-  if (b <= 32) chol_reg_from_partials<1>(w, G, nsplit, b, t);
-  else if (b <= 64) chol_reg_from_partials<2>(w, G, nsplit, b, t);
-  else if (b <= CREG_BMAX) chol_reg_from_partials<3>(w, G, nsplit, b, t);
-  else {
+  {
     // sum of the split-K partial Gram matrices; (row, column) from the warp / lane, no integer division, all partials of
     // several rows in flight at once
     const int lane = t & 31, wp = t >> 5, nw = nt >> 5;
@@ -505,16 +544,17 @@ __global__ void __launch_bounds__(512) chol_kernel(cplx* __restrict__ base, long
     __syncthreads();
     chol_factor(w, b, t, nt);
   }
-  cplx* R = cb + R_;
-  for (int r = t >> 5; r < b; r += nt >> 5)
-    for (int c = t & 31; c < b; c += 32) R[(long long)r * b + c] = c >= r ? S[r * ld + c] : cmake(0.0, 0.0);
-  cplx* Dv = cb + Dinv_;
-  for (int i = t; i < b; i += nt) Dv[i] = cmake(w.dinv[i], 0.0);
-  chol_diag_inverses(w, b, cb + Xd_, t, nt);
-  if (t < 32) {
-    const double mn = chol_min_pivot(w, b, t);
-    if (t == 0) stat[blockIdx.x] = fmin(stat[blockIdx.x], mn);
-  }
+  chol_kernel_tail(w, cb, g, stat, t, nt);
+}
+
+static void launch_chol(const Arena& a, int64_t Gp, int split, int64_t R_out, int64_t Dinv, int64_t Xd, int b, double* stat) {
+  const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 3 * sizeof(double) * (size_t)b + 32;
+  const CholArgs g{Gp, R_out, Dinv, Xd, split, b, a.mask, a.mask_want};
+  if (b <= 32) chol_reg_kernel<1><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
+  else if (b <= 64) chol_reg_kernel<2><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
+  else if (b <= CREG_BMAX) chol_reg_kernel<3><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
+  else chol_blocked_kernel<<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
+  ++*a.launches;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -715,7 +755,7 @@ static int cholqr_cluster_rl(int64_t rows, int b) {
 // The X_pp, the blocks of R above the diagonal and the solved entries live in shared memory.
 constexpr int TRSM_ROWS = 16;
 
-__global__ void __launch_bounds__(512) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
+__global__ void __launch_bounds__(512, 2) trsm_kernel(cplx* __restrict__ base, long long chain_stride, long long Y_, long long R_, long long Xd_,
                                                    long long Out_, int rows, int b, const int* __restrict__ mask, int mask_want) {
   if (mask && mask[blockIdx.y] != mask_want) return;
   extern __shared__ __align__(16) unsigned char tr_raw[];
@@ -1030,10 +1070,8 @@ static int64_t cholqr_pass_narrow(const Arena& a, int64_t Y, int64_t T, int64_t 
   const int split = rows >= 256 ? GRAM_SPLIT : 1;
   gemm_splitk(a, Gp, Y, Y, b, b, rows, OP_C, OP_N, split);
   PM(1);
-  const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 3 * sizeof(double) * (size_t)b + 32;
   const int64_t Xd = Dinv + b;                                     // diagonal-block inverses behind the 1/diagonal entries
-  chol_kernel<<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, Gp, split, R_out, Dinv, Xd, b, stat, a.mask, a.mask_want);
-  ++*a.launches;
+  launch_chol(a, Gp, split, R_out, Dinv, Xd, b, stat);
   PM(2);
   if (T >= 0) {                                                   // T < 0: only R is wanted
     const int nblk = (b + CNB - 1) / CNB;
@@ -1090,29 +1128,23 @@ static int64_t cholqr_pass(const Arena& a, int64_t Y, int64_t T, int64_t Gp, int
 // Cholesky-QR squares the condition number, so it is used only where that is harmless: the pivots are invariant under
 // column scaling, and the smallest pivot / diagonal of pass 1 bounds 1 / cond^2 of the column-scaled matrix.  With a ratio
 // >= CHOLQR2_MIN_PIVOT the first pass leaves ||Q1^H Q1 - I|| <~ eps / ratio <= 1e-5 and the second pass brings it to eps.
-// Anything else -- smaller pivots, numerically dependent (dropped) columns, non-finite entries -- is decided ON THE DEVICE and
-// sends the whole op to the Householder kernels (IF node of the program's graph; host-driven mode reads the flag back).
+// Anything else -- smaller pivots, numerically dependent (dropped) columns, non-finite entries -- is decided ON THE DEVICE, per
+// chain, and redone by the Householder kernels, which are launched behind the decision with that per-chain predicate.
 // The boundary-MPS sites of a converged BP run have scaled condition numbers of 1e2 .. 1e6 (measured on the op streams of
 // the CPU tier); the rank-deficient sites of the first iterations from product messages take the fallback.
 constexpr double CHOLQR2_MIN_PIVOT = 1e-11;
 
-__global__ void cholqr2_decide_kernel(SvdCtl* __restrict__ ctl, const double* __restrict__ stat, const cplx* __restrict__ base, long long chain_stride,
-                                      long long R1_, long long R2_, int n, int nb, cudaGraphConditionalHandle h_if, int use_handles) {
-  // one warp: lanes over the diagonal entries
-  int bad = 0;
-  for (int c = 0; c < nb; ++c) {
-    const double pv = stat[c];
-    if (!(pv >= CHOLQR2_MIN_PIVOT)) bad = 1;                       // also NaN
-    const cplx* R1 = base + (long long)c * chain_stride + R1_;
-    const cplx* R2 = base + (long long)c * chain_stride + R2_;
-    for (int j = threadIdx.x; j < n; j += 32)
-      if (!(R1[(long long)j * n + j].x > 0.0) || !(R2[(long long)j * n + j].x > 0.0)) bad = 1;     // dropped column
-  }
+__global__ void cholqr2_decide_kernel(int* __restrict__ state, const double* __restrict__ stat, const cplx* __restrict__ base, long long chain_stride,
+                                      long long R1_, long long R2_, int n) {
+  // one warp per chain: lanes over the diagonal entries
+  const int c = blockIdx.x;
+  int bad = !(stat[c] >= CHOLQR2_MIN_PIVOT);                         // also NaN
+  const cplx* R1 = base + (long long)c * chain_stride + R1_;
+  const cplx* R2 = base + (long long)c * chain_stride + R2_;
+  for (int j = threadIdx.x; j < n; j += 32)
+    if (!(R1[(long long)j * n + j].x > 0.0) || !(R2[(long long)j * n + j].x > 0.0)) bad = 1;       // dropped column
   bad = __any_sync(0xffffffffu, bad);
-  if (threadIdx.x == 0) {
-    ctl->any_exact = bad;
-    if (use_handles) cudaGraphSetConditional(h_if, bad ? 1u : 0u);
-  }
+  if (threadIdx.x == 0) state[c] = bad ? CHAIN_EXACT : CHAIN_ACCEPTED;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1125,7 +1157,7 @@ constexpr double TSVD_PIVOT_TRUST = 1e-3;
 __global__ void tsvd_decide_kernel(SvdCtl* __restrict__ ctl, int* __restrict__ state, double* __restrict__ stat, const double* __restrict__ resid,
                                    const double* __restrict__ ratio, const double* __restrict__ discf, int nb, int first, int max_rounds,
                                    int iters_first, int iters_more, cudaGraphConditionalHandle h_loop, cudaGraphConditionalHandle h_exact,
-                                   int use_handles) {
+                                   int use_handles, int spec) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int round = first ? 1 : ctl->round + 1;
   int any_run = 0, any_exact = 0;
@@ -1157,6 +1189,7 @@ __global__ void tsvd_decide_kernel(SvdCtl* __restrict__ ctl, int* __restrict__ s
     cudaGraphSetConditional(h_loop, any_run ? 1u : 0u);
     cudaGraphSetConditional(h_exact, any_exact ? 1u : 0u);
   }
+  if (spec && (any_run || any_exact)) ctl->spec_fail = 1;        // speculative graph: nothing follows up on this op; the run is void
 }
 
 int svd_exact(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep, int nr_bulk,
@@ -1268,7 +1301,7 @@ static void tsvd_more_round(const Arena& a, const TsvdBufs& w, int64_t A, int64_
   // TSVD_IT_MORE odd: cur == Qb again
   rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, cur, f0, f1, true);
   tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 0,
-                                             max_rounds, iters_first, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0);
+                                             max_rounds, iters_first, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0, 0);
   ++*a.launches;
 }
 
@@ -1289,9 +1322,20 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   // An op that needed r > 1 rounds when its program ran host-driven (previous BP iteration: nearly the same spectrum) gets
   // the iterations of those rounds up front in the captured graph: one Rayleigh-Ritz step + check instead of r.
   int it_cold = it_default;
+  // SPECULATIVE capture (Arena::speculate): an op whose host-driven run was settled by the subspace iteration within four
+  // rounds gets that schedule plus `spec_slack` iterations and NO conditional node -- a conditional node makes the GPU drain
+  // every kernel in flight, also those of the other program graphs running beside this one (six side programs: each of the
+  // ~550 nodes per chain waited for some other chain's 300 us Jacobi kernel).  The acceptance test still runs; a miss
+  // raises SvdCtl::spec_fail and the host reruns the program host-driven, which also re-learns the schedule.
+  static const int spec_slack = getenv("KBP_TSVD_SPEC_SLACK") ? atoi(getenv("KBP_TSVD_SPEC_SLACK")) : 1;
+  bool spec = false;
   if (learn && a0.capture && a0.tsvd_rounds) {
     auto f = a0.tsvd_rounds->find(a0.op_key);
     if (f != a0.tsvd_rounds->end() && f->second > 1) it_cold = it_default + ((f->second < 4 ? f->second : 4) - 1) * TSVD_IT_MORE;
+    if (a0.speculate && f != a0.tsvd_rounds->end() && f->second >= 1 && f->second <= 4) {
+      spec = true;
+      it_cold += spec_slack;
+    }
   }
   // cold start: after `safe0` SAFE iterations the block is already ordered well enough (contamination of column j by a
   // larger direction i has decayed as (s_j/s_i)^(2k), one fast step amplifies it by (s_i/s_j)^2) for the FAST form
@@ -1319,7 +1363,7 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   w.Pb = o;               // m x n: P = US Vh
   double* stat = a.svd_off;          // [nb] min pivot ratio, then [nb] each: residual, ratio, discarded fraction, [2 nb] norms, partial sums
   double* norms = a.svd_off + 4 * a.nb;
-  const cudaGraphConditionalHandle h_loop = new_cond_handle(a), h_exact = new_cond_handle(a);
+  const cudaGraphConditionalHandle h_loop = spec ? 0 : new_cond_handle(a), h_exact = spec ? 0 : new_cond_handle(a);
 
   // ---- round 1: pseudo-random block, it_cold iterations
   int64_t Qb = w.panel[0], f0 = w.panel[1], f1 = w.panel[2], f2 = w.panel[3];
@@ -1367,12 +1411,13 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   }
   rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, Qb, f0, f1, cold_fast);
   tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 1,
-                                             max_rounds, it_cold, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0);
+                                             max_rounds, it_cold, TSVD_IT_MORE, h_loop, h_exact, (a.capture && !spec) ? 1 : 0, spec ? 1 : 0);
   ++*a.launches;
 
   // ---- further rounds while some chain is RUNNING; only those chains take part
   int rounds = 1;
-  if (a.capture) {
+  if (spec) {
+  } else if (a.capture) {
     Arena body;
     if (!begin_cond_body(a, h_loop, true, &body)) return -1;
     body.mask = a.chain_state; body.mask_want = CHAIN_RUNNING;
@@ -1396,7 +1441,9 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
                                                                     norms, a.chain_state, CHAIN_ACCEPTED);
   ++*a.launches;
   // ---- chains the iteration could not settle: exact block-Jacobi SVD of the same matrix
-  if (a.capture) {
+  bool used_exact = false;
+  if (spec) {
+  } else if (a.capture) {
     Arena body;
     if (!begin_cond_body(a, h_exact, false, &body)) return -1;
     body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
@@ -1407,8 +1454,10 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
     Arena body = a;
     body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
     if (svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc) < 0) return -1;
+    used_exact = true;
   }
-  if (!a.capture && a.tsvd_rounds) (*a.tsvd_rounds)[a.op_key] = rounds;
+  // what the captured program gives this op: `rounds` iterations up front; 0 = it needed the exact path (keeps its nodes)
+  if (!a.capture && a.tsvd_rounds) (*a.tsvd_rounds)[a.op_key] = used_exact ? 0 : rounds;
   return rounds;
 }
 
@@ -1416,13 +1465,12 @@ void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t wor
 
 bool qr_cholqr2(const Arena& a0, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   static const bool on = !(getenv("KBP_QR_CHOLQR2") && atoi(getenv("KBP_QR_CHOLQR2")) == 0);
-  if (!on || n < 8 || n > CREG_BMAX || m < 4 * n) return false;
+  if (!on || a0.mask != nullptr || n < 8 || n > CREG_BMAX || m < 4 * n) return false;
   const int b = (int)n, nblk = (b + CNB - 1) / CNB;
   const int64_t bb = n * n, need = m * n + GRAM_SPLIT * bb + 2 * bb + n + (int64_t)nblk * CNB * CNB + 8;
   const int64_t k = n;
   if (need > m * n + m * k + k + 8) return false;                  // the op's workspace (kbp_qr_work_elems)
   Arena a = a0;
-  a.mask = nullptr;
   const int64_t T1 = work, Gp = T1 + m * n, R1 = Gp + GRAM_SPLIT * bb, R2 = R1 + bb, Dinv = R2 + bb;
   double* stat = a.svd_off;
   tsvd_fill_kernel<<<(a.nb + 127) / 128, 128, 0, a.stream>>>(stat, a.nb, 1.0);
@@ -1430,24 +1478,24 @@ bool qr_cholqr2(const Arena& a0, int64_t A, int64_t Q, int64_t R, int64_t work, 
   cholqr_pass_narrow(a, A, T1, Gp, Dinv, R1, m, b, stat);          // A = Q1 R1
   cholqr_pass_narrow(a, T1, Q, Gp, Dinv, R2, m, b, stat);          // Q1 = Q R2
   gemm(a, R, R2, R1, n, n, n, OP_N, OP_N);                         // R = R2 R1 (upper triangular)
-  const cudaGraphConditionalHandle h_if = new_cond_handle(a);
-  cholqr2_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, stat, a.base, a.chain_stride, R1, R2, b, a.nb, h_if, a.capture ? 1 : 0);
+  cholqr2_decide_kernel<<<a.nb, 32, 0, a.stream>>>(a.chain_state, stat, a.base, a.chain_stride, R1, R2, b);
   ++*a.launches;
-  if (a.capture) {
-    Arena body;
-    if (!begin_cond_body(a, h_if, false, &body)) { qr_householder(a, A, Q, R, work, m, n); return true; }   // cannot nest deeper: stable path unconditionally
-    qr_householder(body, A, Q, R, work, m, n);
-    end_body(body);
-  } else {
-    if (read_ctl(a) != cudaSuccess) return true;
-    if (a.ctl_host->any_exact) qr_householder(a, A, Q, R, work, m, n);
-  }
+  // the Householder launches are ALWAYS issued, predicated per chain on the decision above: a chain that passed costs one
+  // empty launch.  (An IF node per QR op made concurrently running program graphs serialise each other: six side programs
+  // of the N = 6 block went from 730 to 1460 ms per BP iteration.)
+  Arena body = a;
+  body.mask = a.chain_state;
+  body.mask_want = CHAIN_EXACT;
+  qr_householder(body, A, Q, R, work, m, n);
   return true;
 }
 
 void init_tsvd_attributes() {
   cudaFuncSetAttribute(cholqr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);   // + 8 KB static shared memory <= 227 KB
-  cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);
+  cudaFuncSetAttribute(chol_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(chol_reg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(chol_reg_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);
+  cudaFuncSetAttribute(chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);
   cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
 }
 

@@ -20,7 +20,7 @@ EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
     "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
-    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
+    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_spec_failed", "kbp_run_relearn", "kbp_set_speculation", "kbp_spec_counters", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
 ]
 
 
@@ -68,6 +68,10 @@ def load_library():
         lib.kbp_run.argtypes = [P, P, L]; lib.kbp_run.restype = I
         lib.kbp_graph_ready.argtypes = [P, P, L]; lib.kbp_graph_ready.restype = I
         lib.kbp_graph_counters.argtypes = [P, P]; lib.kbp_graph_counters.restype = I
+        lib.kbp_spec_failed.argtypes = [P]; lib.kbp_spec_failed.restype = I
+        lib.kbp_run_relearn.argtypes = [P, P, L]; lib.kbp_run_relearn.restype = I
+        lib.kbp_set_speculation.argtypes = [P, I]; lib.kbp_set_speculation.restype = I
+        lib.kbp_spec_counters.argtypes = [P, P]; lib.kbp_spec_counters.restype = I
         lib.kbp_graph_policy.argtypes = [P, L, I]; lib.kbp_graph_policy.restype = I
         for nm in ("kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr"):
             getattr(lib, nm).argtypes = [P]; getattr(lib, nm).restype = ctypes.c_uint64
@@ -184,6 +188,32 @@ class Engine:
     def run(self, words: np.ndarray, soft_errors=()):
         w = np.ascontiguousarray(words, dtype=np.int64)
         return self._check(self.lib.kbp_run(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)), soft=soft_errors)
+
+    def spec_failed(self) -> bool:
+        """waits for the stream.  True: the program last started by ``run`` was a speculative graph (fixed SVD schedules, no
+        conditional nodes) and one of its truncations missed its acceptance test -- rerun it with ``run_relearn`` before
+        using anything it wrote (include/kbp.h)."""
+        return bool(self.lib.kbp_spec_failed(self.h))
+
+    def run_relearn(self, words: np.ndarray, soft_errors=()):
+        w = np.ascontiguousarray(words, dtype=np.int64)
+        return self._check(self.lib.kbp_run_relearn(self.h, w.ctypes.data_as(ctypes.c_void_p), int(w.size)), soft=soft_errors)
+
+    def run_verified(self, words: np.ndarray, soft_errors=()):
+        """``run`` + wait + the speculative-graph protocol: on a missed acceptance test the program is rerun host-driven."""
+        rc = self.run(words, soft_errors=soft_errors)
+        if self.spec_failed():
+            self.slots_zero()
+            rc = self.run_relearn(words, soft_errors=soft_errors)
+        return rc
+
+    def set_speculation(self, on: bool):
+        self._check(self.lib.kbp_set_speculation(self.h, 1 if on else 0))
+
+    def spec_counters(self) -> dict:
+        out = np.zeros(2, dtype=np.int64)
+        self._check(self.lib.kbp_spec_counters(self.h, out.ctypes.data_as(ctypes.c_void_p)))
+        return {"spec_launches": int(out[0]), "spec_failures": int(out[1])}
 
     def graph_ready(self, words: np.ndarray) -> bool:
         """True: the next ``run`` of this program is one asynchronous CUDA-graph launch (no host decisions)."""

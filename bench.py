@@ -470,7 +470,11 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    ms_ranks = [ms_step]
     if world > 1:
+        allms = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms_step], device="cuda", dtype=torch.float64))
+        ms_ranks = [float(x[0]) for x in allms]           # every rank works on its own unit cell (different spectra): the step is their max
         t = torch.tensor([ms_step, ms_e2e, ms_sharded or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, ms_e2e = float(t[0]), float(t[1])
@@ -496,6 +500,7 @@ def main():
                        "l2": "512 MiB buffer rewritten between timed iterations (L2 flush)",
                        "swallows_per_message": len(bp.contraction_order.kagome_order(N, "D", "ToMessage")) - 1},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ss.h2d), "d2h_bytes_per_step": int(ss.d2h), "ms_per_step": ms_e2e},
+            "ms_per_step_by_rank": ms_ranks,
             "gpu_launches": int(n_launch),
             "graph_launches": int(g1["graph_replays"] - g0["graph_replays"]) * (world if world > 1 else 1),
             "host_launches_per_step": (g1["graph_replays"] - g0["graph_replays"]) / a.steps,

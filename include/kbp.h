@@ -96,6 +96,8 @@ int kbp_sync(kbp_ctx* ctx);
 int kbp_spec_failed(kbp_ctx* ctx);
 int kbp_run_relearn(kbp_ctx* ctx, const int64_t* words, int64_t n_words);
 int kbp_set_speculation(kbp_ctx* ctx, int on);
+/* developer probe (KBP_KTIME=1 in the environment): print and reset the in-kernel wall time of the Cholesky CTAs */
+int kbp_ktime_report(kbp_ctx* ctx, const char* tag);
 int kbp_spec_counters(const kbp_ctx* ctx, int64_t* out2);
 
 /* device addresses of the arena ([nb][chain_elems] complex128), of the slot table ([nb][n_slots] doubles) and the CUDA stream

@@ -15,7 +15,11 @@
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
 
 namespace kbp {
 
@@ -33,7 +37,17 @@ struct GemmArgs {
   int* counters;                  // [nb][GEMM_MAX_TILES], zero between launches
   const int* mask;                // per-chain predicate (kbp_ops.cuh: Arena::mask)
   int mask_want;
+  int ktime_slot;                 // developer probe (KBP_KTIME=1): slot of this launch in the device time table, -1 = off
 };
+
+// developer probe: first CTA start / last CTA end of every GEMM launch by %globaltimer (KBP_KTIME=1)
+constexpr int GEMM_KT_SLOTS = 1 << 16;
+__device__ unsigned long long g_gemm_t0[GEMM_KT_SLOTS], g_gemm_t1[GEMM_KT_SLOTS];
+__device__ __forceinline__ unsigned long long gemm_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int GEMM_MAX_TILES = 4096;
 
@@ -60,6 +74,7 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
 
   const int chain = blockIdx.z / g.ksplit, split = blockIdx.z - chain * g.ksplit;
   if (g.mask && g.mask[chain] != g.mask_want) return;
+  if (g.ktime_slot >= 0 && threadIdx.x == 0) atomicMin(&g_gemm_t0[g.ktime_slot], gemm_globaltimer());
   cplx* Cb = base + (long long)chain * chain_stride + g.C + (long long)split * g.m * g.n;
   const cplx* Ab = base + (long long)chain * chain_stride + g.A;
   const cplx* Bb = base + (long long)chain * chain_stride + g.B;
@@ -178,6 +193,7 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
     }
   }
   cp_async_wait<0>();
+  if (g.ktime_slot >= 0 && threadIdx.x == 0) atomicMax(&g_gemm_t1[g.ktime_slot], gemm_globaltimer());   // (epilogue not included)
   if (g.fused) {
     // split-K without a second launch: every CTA parks its partial tile, the last one to arrive at the tile's counter adds
     // the ksplit partials in fixed order (bitwise deterministic) and writes C
@@ -259,7 +275,10 @@ static void launch_gemm(const Arena& a, const GemmArgs& g) {
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
   if (m == 0 || n == 0) return;
-  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev, a.mask, a.mask_want};
+  static const bool ktime = getenv("KBP_KTIME") != nullptr;
+  static int kt_next = 0;                                     // (probe runs are single-threaded at capture time)
+  GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev, a.mask, a.mask_want,
+             (ktime && m * n * k >= 8 * 1024 * 1024) ? (kt_next++ % GEMM_KT_SLOTS) : -1};
   if (ksplit == 0) {
     // automatic: a small product is bound by how many warps (16x8 accumulator tiles) it offers to the 592 sub-partitions;
     // split k (fused, deterministic reduction) until there are enough, keeping >= 4 slabs per split
@@ -286,6 +305,7 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
   static const int fused_tile = getenv("KBP_GEMM_FUSED_TILE") ? atoi(getenv("KBP_GEMM_FUSED_TILE")) : 16;
   static const int stages16 = getenv("KBP_GEMM_STAGES16") ? atoi(getenv("KBP_GEMM_STAGES16")) : 3;   // measured: 3 stages (30 KB, 7 CTAs per SM) beat 4 on every shape of tools/gemm_bench.py d4
   if (g.fused && fused_tile == 32) launch_gemm<32, 32, 4, 8>(a, g);
+  else if (stages16 == 2 && (g.fused || ctas32 < 96)) launch_gemm<16, 16, 2, 2>(a, g);
   else if (stages16 == 3 && (g.fused || ctas32 < 96)) launch_gemm<16, 16, 3, 2>(a, g);
   else if (g.fused) launch_gemm<16, 16, 4, 2>(a, g);
   else if (ctas64 >= 96) launch_gemm<64, 64, 3, 8>(a, g);
@@ -304,9 +324,25 @@ static void gemm_attr() {
   cudaFuncSetAttribute(zgemm_dmma_kernel<BM, BN, STAGES, NWARPS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
+void gemm_ktime_report(const char* tag) {
+  static std::vector<unsigned long long> t0(GEMM_KT_SLOTS), t1(GEMM_KT_SLOTS);
+  cudaMemcpyFromSymbol(t0.data(), g_gemm_t0, sizeof(unsigned long long) * GEMM_KT_SLOTS);
+  cudaMemcpyFromSymbol(t1.data(), g_gemm_t1, sizeof(unsigned long long) * GEMM_KT_SLOTS);
+  double sum = 0;
+  long long n = 0;
+  for (int i = 0; i < GEMM_KT_SLOTS; ++i)
+    if (t1[i] > t0[i] && t0[i] != ~0ull) { sum += (double)(t1[i] - t0[i]); ++n; }
+  if (n) fprintf(stderr, "[kbp ktime] %s: %lld large GEMM launches (last replay), %.2f us each from first CTA start to last CTA main loop end\n", tag, n, 1e-3 * sum / n);
+  std::fill(t0.begin(), t0.end(), ~0ull);
+  std::fill(t1.begin(), t1.end(), 0ull);
+  cudaMemcpyToSymbol(g_gemm_t0, t0.data(), sizeof(unsigned long long) * GEMM_KT_SLOTS);
+  cudaMemcpyToSymbol(g_gemm_t1, t1.data(), sizeof(unsigned long long) * GEMM_KT_SLOTS);
+}
+
 void init_gemm_attributes() {
   gemm_attr<16, 16, 4, 2>();
   gemm_attr<16, 16, 3, 2>();
+  gemm_attr<16, 16, 2, 2>();
   gemm_attr<32, 32, 4, 8>();
   gemm_attr<64, 64, 3, 8>();
 }

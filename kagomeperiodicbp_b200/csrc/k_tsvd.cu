@@ -470,6 +470,7 @@ struct CholArgs {
   int nsplit, b;
   const int* mask;
   int mask_want;
+  int ktime;
 };
 
 __device__ __forceinline__ void chol_kernel_tail(const CholWork& w, cplx* cb, const CholArgs& g, double* __restrict__ stat, int t, int nt) {
@@ -498,9 +499,19 @@ __device__ __forceinline__ CholWork chol_work(unsigned char* raw, cplx* rowbuf, 
   return w;
 }
 
+// developer probe (KBP_KTIME=1): wall time of every Cholesky CTA by %globaltimer, summed on the device -- the same one-SM kernel
+// timed alone and with other program graphs running beside it shows how much the neighbours' work on its SM costs it
+__device__ unsigned long long g_ktime_ns = 0, g_ktime_n = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int NC>
 __global__ void __launch_bounds__(512, NC <= 2 ? 2 : 1) chol_reg_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
   if (g.mask && g.mask[blockIdx.x] != g.mask_want) return;
+  const unsigned long long kt0 = g.ktime ? globaltimer_ns() : 0ull;
   extern __shared__ __align__(16) unsigned char ch_raw[];
   __shared__ cplx rowbuf[4 * CREG_LINE];
   const CholWork w = chol_work(ch_raw, rowbuf, g.b);
@@ -508,6 +519,23 @@ __global__ void __launch_bounds__(512, NC <= 2 ? 2 : 1) chol_reg_kernel(cplx* __
   const int t = threadIdx.x;
   chol_reg_from_partials<NC>(w, cb + g.G, g.nsplit, g.b, t);
   chol_kernel_tail(w, cb, g, stat, t, blockDim.x);
+  if (g.ktime) {
+    __syncthreads();
+    if (t == 0) { atomicAdd(&g_ktime_ns, globaltimer_ns() - kt0); atomicAdd(&g_ktime_n, 1ull); }
+  }
+}
+
+void gemm_ktime_report(const char* tag);
+
+void ktime_report(const char* tag) {
+  gemm_ktime_report(tag);
+  unsigned long long ns = 0, n = 0;
+  cudaMemcpyFromSymbol(&ns, g_ktime_ns, sizeof(ns));
+  cudaMemcpyFromSymbol(&n, g_ktime_n, sizeof(n));
+  if (n) fprintf(stderr, "[kbp ktime] %s: %llu Cholesky CTAs, %.2f us each (globaltimer, inside the kernel)\n", tag, n, 1e-3 * (double)ns / (double)n);
+  ns = n = 0;
+  cudaMemcpyToSymbol(g_ktime_ns, &ns, sizeof(ns));
+  cudaMemcpyToSymbol(g_ktime_n, &n, sizeof(n));
 }
 
 __global__ void __launch_bounds__(512) chol_blocked_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
@@ -549,7 +577,8 @@ __global__ void __launch_bounds__(512) chol_blocked_kernel(cplx* __restrict__ ba
 
 static void launch_chol(const Arena& a, int64_t Gp, int split, int64_t R_out, int64_t Dinv, int64_t Xd, int b, double* stat) {
   const size_t smem = sizeof(double2) * (size_t)b * (b + 1) + 3 * sizeof(double) * (size_t)b + 32;
-  const CholArgs g{Gp, R_out, Dinv, Xd, split, b, a.mask, a.mask_want};
+  static const int ktime = getenv("KBP_KTIME") != nullptr;
+  const CholArgs g{Gp, R_out, Dinv, Xd, split, b, a.mask, a.mask_want, ktime};
   if (b <= 32) chol_reg_kernel<1><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
   else if (b <= 64) chol_reg_kernel<2><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);
   else if (b <= CREG_BMAX) chol_reg_kernel<3><<<a.nb, 512, smem, a.stream>>>(a.base, a.chain_stride, g, stat);

@@ -494,6 +494,15 @@ int kbp_run_relearn(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   return run_ops(c, w, n_words, false, nullptr, h);
 }
 
+/* developer probe (KBP_KTIME=1): prints and resets the in-kernel timing of the Cholesky CTAs (k_tsvd.cu) */
+int kbp_ktime_report(kbp_ctx* c, const char* tag) {
+  if (!c) return KBP_E_ARG;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  kbp::ktime_report(tag ? tag : "");
+  return KBP_OK;
+}
+
 int kbp_set_speculation(kbp_ctx* c, int on) {
   if (!c) return KBP_E_ARG;
   c->speculate = on != 0;

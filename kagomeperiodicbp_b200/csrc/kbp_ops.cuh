@@ -109,6 +109,7 @@ bool qr_cluster(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t m, int6
 // work: see svd_work_elems().  Returns the number of Jacobi sweeps used (max over chains), <0 on failure.
 int svd_truncate(const Arena& a, int64_t A, int64_t US, int64_t Vh, int64_t work, int64_t m, int64_t n, int64_t keep,
                  int nr_bulk, int slot_lognorm, int slot_trunc);
+void ktime_report(const char* tag);
 // opt-in of every kernel to > 48 KB of dynamic shared memory on the CURRENT device (called once per device by kbp_create)
 void init_device_attributes();
 // conditional node (WHILE or IF) appended to the capture in progress on a.stream; the returned Arena launches into its body.

@@ -20,7 +20,7 @@ EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
     "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
-    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_spec_failed", "kbp_run_relearn", "kbp_set_speculation", "kbp_spec_counters", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
+    "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_spec_failed", "kbp_run_relearn", "kbp_set_speculation", "kbp_spec_counters", "kbp_ktime_report", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library():
         lib.kbp_run_relearn.argtypes = [P, P, L]; lib.kbp_run_relearn.restype = I
         lib.kbp_set_speculation.argtypes = [P, I]; lib.kbp_set_speculation.restype = I
         lib.kbp_spec_counters.argtypes = [P, P]; lib.kbp_spec_counters.restype = I
+        lib.kbp_ktime_report.argtypes = [P, ctypes.c_char_p]; lib.kbp_ktime_report.restype = I
         lib.kbp_graph_policy.argtypes = [P, L, I]; lib.kbp_graph_policy.restype = I
         for nm in ("kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr"):
             getattr(lib, nm).argtypes = [P]; getattr(lib, nm).restype = ctypes.c_uint64
@@ -206,6 +207,9 @@ class Engine:
             self.slots_zero()
             rc = self.run_relearn(words, soft_errors=soft_errors)
         return rc
+
+    def ktime_report(self, tag: str = ""):
+        self.lib.kbp_ktime_report(self.h, tag.encode())
 
     def set_speculation(self, on: bool):
         self._check(self.lib.kbp_set_speculation(self.h, 1 if on else 0))

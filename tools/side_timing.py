@@ -42,10 +42,14 @@ for s in BLOCK_SIDES_CCW:                      # first sight + capture
     for _ in range(2):
         comps[s].run_resident(engs[s], (-4,))
         engs[s].sync()
+if os.environ.get("KBP_KTIME"):
+    engs["D"].ktime_report("(reset after warm-up)")
 for k in (1, 2, 3, 6):
     sides = BLOCK_SIDES_CCW[:k]
     best = 1e9
-    for rep in range(3):
+    if os.environ.get("KBP_KTIME"):                # the probe tables hold one replay
+        engs["D"].ktime_report("(reset)")
+    for rep in range(1 if os.environ.get("KBP_KTIME") else 3):
         t0 = time.perf_counter()
         host = []
         if "--threads" in sys.argv:                    # one launching thread per side (graph launches of big programs take host time)
@@ -58,7 +62,7 @@ for k in (1, 2, 3, 6):
             h0 = time.perf_counter()
             comps[s].run_resident(engs[s], (-4,))
             host.append(time.perf_counter() - h0)
-        if rep == 2 and k == 6:
+        if k == 6:
             print("  host time of the six graph launches (ms):", " ".join(f"{1e3*x:.1f}" for x in host))
         for s in sides:
             engs[s].sync()
@@ -67,4 +71,6 @@ for k in (1, 2, 3, 6):
                 print(f"  (side {s}: speculative graph missed an acceptance test, rerun host-driven)")
         best = min(best, time.perf_counter() - t0)
     print(f"{k} side(s) concurrently, {B} cell(s) per launch: {best*1e3:.1f} ms per iteration")
+    if os.environ.get("KBP_KTIME"):
+        engs["D"].ktime_report(f"{k} side(s)")
 print(engs["D"].svd_counters(), engs["D"].spec_counters())

@@ -10,8 +10,7 @@
 // no atomics).  Operands stay in the layout they have in HBM -- "k-contiguous" [row][k] or
 // "m-contiguous" [k][row] depending on op -- so every copy is coalesced and transposition / conjugation
 // happen in the fragment loads: one LDS.128 brings (re, im) of an element, conflict-free for both layouts
-// (row strides of 20 resp. BM+2 elements).  The complex product is four real DMMAs per (tile, k8):
-//     Cr += Ar*Br - Ai*Bi ;  Ci += Ar*Bi + Ai*Br.
+// (row strides of 20 resp. BM+2 elements).  The complex product is THREE real DMMAs per (tile, k8) (3M form, see the kernel).
 #include "kbp_common.cuh"
 #include "kbp_ops.cuh"
 
@@ -138,17 +137,20 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
     }
   };
 
-  // FP64 DMMA has a long dependent-issue latency: with one accumulator tile per warp (the small-tile configurations) the
-  // four products of a complex MAC and consecutive k8 steps would form one serial chain per slab.  They get independent
-  // accumulators (2 products x 2 k8 parities) that are added up in the epilogue.
-  constexpr int NACC = (NT <= 2) ? 4 : 1;
-  double cr[NACC][NT][4], ci[NACC][NT][4];
+  // The complex product takes THREE real DMMAs per (tile, k8) instead of four (the "3M" form):
+  //     P1 += Ar Br ;  P2 += Ai Bi ;  P3 += (Ar + Ai)(Br + Bi)        ->   Cr = P1 - P2 ,  Ci = P3 - P1 - P2
+  // -- a quarter less work on the FP64 pipe, which DMMA shares with every DFMA of the one-SM kernels running beside the
+  // products of other chains; the two fragment sums cost one DADD per loaded element.  Normwise as accurate as the four-product
+  // form (|dC| <~ k eps |A| |B|).  FP64 DMMA also has a long dependent-issue latency: the three products are independent
+  // chains, and the small-tile configurations (NT <= 2) keep a second set for the odd k8 steps, added up in the epilogue.
+  constexpr int NACC = (NT <= 2) ? 2 : 1;
+  double p1[NACC][NT][4], p2[NACC][NT][4], p3[NACC][NT][4];
 #pragma unroll
   for (int q4 = 0; q4 < NACC; ++q4)
 #pragma unroll
     for (int i = 0; i < NT; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cr[q4][i][j] = ci[q4][i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) p1[q4][i][j] = p2[q4][i][j] = p3[q4][i][j] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -164,31 +166,30 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
     const cplx* bt = Bs + (slab % STAGES) * TB;
 #pragma unroll
     for (int ks = 0; ks < BK / 8; ++ks) {
-      double ar[4], aim[4], an[4];
+      double ar[4], aim[4], as[4];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         const int mm = wm * 16 + gq + 8 * (v & 1), kk = ks * 8 + q + 4 * (v >> 1);
         const cplx x = a_kc ? at[mm * LDK + kk] : at[kk * LDM + mm];
         ar[v] = x.x;
         aim[v] = sa * x.y;
-        an[v] = -aim[v];
+        as[v] = ar[v] + aim[v];
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        double br[2], bi[2];
+        double br[2], bi[2], bs[2];
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const int kk = ks * 8 + q + 4 * v, nn = wn * (NT * 8) + nt * 8 + gq;
           const cplx x = b_kc ? bt[nn * LDK + kk] : bt[kk * LDN + nn];
           br[v] = x.x;
           bi[v] = sb * x.y;
+          bs[v] = br[v] + bi[v];
         }
-        constexpr int A1 = NACC == 4 ? 1 : 0;
-        const int a0 = NACC == 4 ? 2 * (ks & 1) : 0;
-        dmma16x8x8(cr[a0][nt], ar, br);
-        dmma16x8x8(cr[a0 + A1][nt], an, bi);
-        dmma16x8x8(ci[a0][nt], ar, bi);
-        dmma16x8x8(ci[a0 + A1][nt], aim, br);
+        const int a0 = NACC == 2 ? (ks & 1) : 0;
+        dmma16x8x8(p1[a0][nt], ar, br);
+        dmma16x8x8(p2[a0][nt], aim, bi);
+        dmma16x8x8(p3[a0][nt], as, bs);
       }
     }
   }
@@ -206,9 +207,10 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
       for (int v = 0; v < 4; ++v) {
         const int r = row0 + wm * 16 + gq + 8 * (v >> 1);
         const int c = col0 + wn * (NT * 8) + nt * 8 + 2 * q + (v & 1);
-        double sr = cr[0][nt][v], si = ci[0][nt][v];
+        double s1 = p1[0][nt][v], s2 = p2[0][nt][v], s3 = p3[0][nt][v];
 #pragma unroll
-        for (int q4 = 1; q4 < NACC; ++q4) { sr += cr[q4][nt][v]; si += ci[q4][nt][v]; }
+        for (int q4 = 1; q4 < NACC; ++q4) { s1 += p1[q4][nt][v]; s2 += p2[q4][nt][v]; s3 += p3[q4][nt][v]; }
+        const double sr = s1 - s2, si = (s3 - s1) - s2;
         if (r < g.m && c < g.n) part[split * mn + (long long)r * g.n + c] = cmake(sr, si);
       }
     __threadfence();
@@ -243,9 +245,10 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
     for (int v = 0; v < 4; ++v) {
       const int r = row0 + wm * 16 + gq + 8 * (v >> 1);
       const int c = col0 + wn * (NT * 8) + nt * 8 + 2 * q + (v & 1);
-      double sr = cr[0][nt][v], si = ci[0][nt][v];
+      double s1 = p1[0][nt][v], s2 = p2[0][nt][v], s3 = p3[0][nt][v];
 #pragma unroll
-      for (int q4 = 1; q4 < NACC; ++q4) { sr += cr[q4][nt][v]; si += ci[q4][nt][v]; }
+      for (int q4 = 1; q4 < NACC; ++q4) { s1 += p1[q4][nt][v]; s2 += p2[q4][nt][v]; s3 += p3[q4][nt][v]; }
+      const double sr = s1 - s2, si = (s3 - s1) - s2;
       if (r < g.m && c < g.n) Cb[(long long)r * g.n + c] = cmake(sr, si);
     }
 }

@@ -462,9 +462,8 @@ __device__ __forceinline__ void chol_reg_from_smem(const CholWork& w, int b, int
 constexpr int CREG_BMAX = 96;             // widest matrix of the register-resident factorisation (NC = 3: 12 entries per thread)
 
 // One kernel per register-block count NC (and one for the blocked fallback), so that each gets its own register
-// allocation: NC <= 2 (b <= 64: every truncation at D <= 4) fits 64 registers per thread, i.e. HALF an SM's register file.
-// The single kernel before it took 128 x 512 = the whole file: its CTA could only start on an SM with nothing else on it,
-// and with several program graphs in flight (six block sides) it queued behind the other chains' GEMM CTAs.
+// allocation.  (Capping NC = 2 at 64 registers -- half an SM's register file, so that its CTA can start beside other work --
+// was measured: 34 -> 40 us per launch and no gain with six program graphs in flight; the cap is off.)
 struct CholArgs {
   long long G, R, Dinv, Xd;
   int nsplit, b;
@@ -509,7 +508,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int NC>
-__global__ void __launch_bounds__(512, NC <= 2 ? 2 : 1) chol_reg_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
+__global__ void __launch_bounds__(512, 1) chol_reg_kernel(cplx* __restrict__ base, long long chain_stride, CholArgs g, double* __restrict__ stat) {
   if (g.mask && g.mask[blockIdx.x] != g.mask_want) return;
   const unsigned long long kt0 = g.ktime ? globaltimer_ns() : 0ull;
   extern __shared__ __align__(16) unsigned char ch_raw[];

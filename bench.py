@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--ensemble", type=int, default=8, help="unit cells per launch of the extra ensemble measurement at N=1 (0 = skip)")
     ap.add_argument("--ensemble-N", type=int, default=3)
     ap.add_argument("--ite-steps", type=int, default=3, help="ITE steps timed on rank 0 at N=1 (block size min(N, 3)); 0 = skip")
+    ap.add_argument("--seed-offset", type=int, default=0, help="first unit-cell seed of rank 0 (diagnostics: rank r of a multi-GPU run uses seed r * batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
@@ -407,7 +408,7 @@ def main():
     D, N, B = a.D, a.N, a.batch
     chi = 2 * D * D
     cfg = BPConfig(trunc_dim=chi, msg_diff_terminate=1e-6, damping=a.damping, init_msg="UQ")
-    cells = [UnitCell.random(2, D, seed=rank * B + i) for i in range(B)]
+    cells = [UnitCell.random(2, D, seed=a.seed_offset + rank * B + i) for i in range(B)]
     uq = bp.initial_messages(D, N, "UQ")
     msgs_list = [uq] * B
     for _ in range(2):                     # two untimed iterations: messages (and every program shape) reach the steady state
@@ -567,11 +568,11 @@ def main():
             emsgs = [bp.initial_messages(D, EN, "UQ")] * E
             for _ in range(2):
                 emsgs = [r[1] for r in bp.bp_step_batch(EN, ecells, emsgs, cfg, device=dev)]
-            es = SideSet(EN, dev, ecells, emsgs, a.damping)
+            es = SideSet(EN, dev, ecells, emsgs, a.damping, key="ens")
             for _ in range(4):
                 es.step()
             ems = timed_steps(es, 3, flush, barrier, torch)
-            one = SideSet(EN, dev, ecells[:1], emsgs[:1], a.damping)
+            one = SideSet(EN, dev, ecells[:1], emsgs[:1], a.damping, key="ens1")   # own engines: nothing learned from the batch
             for _ in range(4):
                 one.step()
             oms = timed_steps(one, 3, flush, barrier, torch)

@@ -1185,7 +1185,7 @@ constexpr double TSVD_PIVOT_TRUST = 1e-3;
 __global__ void tsvd_decide_kernel(SvdCtl* __restrict__ ctl, int* __restrict__ state, double* __restrict__ stat, const double* __restrict__ resid,
                                    const double* __restrict__ ratio, const double* __restrict__ discf, int nb, int first, int max_rounds,
                                    int iters_first, int iters_more, cudaGraphConditionalHandle h_loop, cudaGraphConditionalHandle h_exact,
-                                   int use_handles, int spec) {
+                                   int use_handles, int spec, const cplx* __restrict__ base, long long chain_stride, long long R1_, int b, int keep) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int round = first ? 1 : ctl->round + 1;
   int any_run = 0, any_exact = 0;
@@ -1195,7 +1195,18 @@ __global__ void tsvd_decide_kernel(SvdCtl* __restrict__ ctl, int* __restrict__ s
       const double pv = stat[c], rs = resid[c], ra = ratio[c], df = discf[c];
       const bool finite = pv == pv && rs == rs && ra == ra && df == df;
       const bool trusted = pv >= TSVD_PIVOT_TRUST;
-      const bool collapse = trusted && ra < TSVD_MIN_RATIO && df > 1e-24;
+      // A kept spectrum that spans more than six decades is only a problem if the block LOST directions of that size: the
+      // Cholesky of the first iterations drops columns it cannot tell from rounding (< ~3e-7 of the leading direction), and
+      // a dropped column stays zero.  If more than `keep` columns of the block are still alive in the Rayleigh-Ritz
+      // factor, the block resolved a direction BELOW the kept ones, i.e. nothing of the kept size was dropped and the kept
+      // set is the dominant one; the small kept directions themselves are as accurate as the large ones (the rounding of
+      // A^H (A q_j) is relative to s_1 s_j: angle error ~ eps s_1 / s_j, contribution to the state ~ eps s_1).
+      int live = 0;
+      {
+        const cplx* R1 = base + (long long)c * chain_stride + R1_;
+        for (int j = 0; j < b; ++j) live += R1[(long long)j * b + j].x > 0.0;
+      }
+      const bool collapse = trusted && ra < TSVD_MIN_RATIO && df > 1e-24 && live <= keep;
       if (finite && trusted && !collapse && rs <= TSVD_RES_TOL) {
         st = CHAIN_ACCEPTED;
         ctl->counters[2] += 1;
@@ -1329,7 +1340,7 @@ static void tsvd_more_round(const Arena& a, const TsvdBufs& w, int64_t A, int64_
   // TSVD_IT_MORE odd: cur == Qb again
   rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, cur, f0, f1, true);
   tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 0,
-                                             max_rounds, iters_first, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0, 0);
+                                             max_rounds, iters_first, TSVD_IT_MORE, h_loop, h_exact, a.capture ? 1 : 0, 0, a.base, a.chain_stride, w.R1, b, (int)keep);
   ++*a.launches;
 }
 
@@ -1439,7 +1450,8 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
   }
   rayleigh_ritz_and_check(a, w, A, US, Vh, m, n, keep, b, Qb, f0, f1, cold_fast);
   tsvd_decide_kernel<<<1, 32, 0, a.stream>>>(a.ctl, a.chain_state, stat, a.svd_off + a.nb, a.svd_off + 2 * a.nb, a.svd_off + 3 * a.nb, a.nb, 1,
-                                             max_rounds, it_cold, TSVD_IT_MORE, h_loop, h_exact, (a.capture && !spec) ? 1 : 0, spec ? 1 : 0);
+                                             max_rounds, it_cold, TSVD_IT_MORE, h_loop, h_exact, (a.capture && !spec) ? 1 : 0, spec ? 1 : 0, a.base, a.chain_stride, w.R1,
+                                             b, (int)keep);
   ++*a.launches;
 
   // ---- further rounds while some chain is RUNNING; only those chains take part
@@ -1478,7 +1490,12 @@ int svd_truncate_subspace(const Arena& a0, int64_t A, int64_t US, int64_t Vh, in
     const int r = svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc);
     if (!end_body(body) || r < 0) return -1;
   } else if (a.ctl_host->any_exact) {
-    if (debug) fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d] exact path after %d rounds\n", (long long)m, (long long)n, (long long)keep, b, rounds);
+    if (debug) {
+      double v[4] = {0, 0, 0, 0};                              // chain 0: pivot ratio, residual, s_keep / s_1, discarded fraction
+      for (int q = 0; q < 4; ++q) cudaMemcpy(&v[q], a.svd_off + q * a.nb, sizeof(double), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[kbp tsvd %lldx%lld keep %lld b %d] exact path after %d rounds: residual %.2e  s_keep/s_1 %.2e  discarded fraction %.2e\n", (long long)m,
+              (long long)n, (long long)keep, b, rounds, v[1], v[2], v[3]);
+    }
     Arena body = a;
     body.mask = a.chain_state; body.mask_want = CHAIN_EXACT;
     if (svd_exact(body, A, US, Vh, work, m, n, keep, nr_bulk, slot_lognorm, slot_trunc) < 0) return -1;

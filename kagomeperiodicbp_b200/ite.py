@@ -82,8 +82,26 @@ def _pinv(B, M, rcond):
     return B.tensordot(VS, U, ([1], [1]), conj_b=True)                                       # V diag(w) U^H
 
 
-def reduced_env(B, Ti, Tj, mps_env):
-    """(ITE.py:853-1302, mps_env branch)  -> X[Di, Dj, DX], ai[d, D, Di], aj[d, D, Dj], Ti_rest, Tj_rest, w (spectrum of N_red)."""
+def rho_from_reduced(N4, ai, aj):
+    """the two-site RDM from the REDUCED environment: with T_i = a_i T_i_rest, T_j = a_j T_j_rest and
+    N4[a, a*, b, b*] = (environment ring contracted with T_i_rest, T_j_rest and their conjugates),
+        rho[p, p*, q, q*] = sum  a_i[p, s, a] conj(a_i[p*, s*, a*])  a_j[q, s, b] conj(a_j[q*, s*, b*])  N4[a, a*, b, b*]
+    is the same contraction as ``rho_ij`` (ITE.py:683-756) in another order -- (d D)^4 numbers on the host instead of a second and
+    third pass over the chi D^2-bond ring tensors (the dominant cost of ``rho_ij``).  Trace normalised."""
+    N4, ai, aj = np.asarray(N4), np.asarray(ai), np.asarray(aj)
+    ket = np.tensordot(ai, aj, ([1], [1]))                                   # [p, a, q, b]
+    t = np.tensordot(ket, N4, ([1, 3], [0, 2]))                              # [p, q, a*, b*]
+    bra = np.conj(ket)                                                       # [p*, a*, q*, b*]
+    rho = np.tensordot(t, bra, ([2, 3], [1, 3]))                             # [p, q, p*, q*]
+    rho = rho.transpose(0, 2, 1, 3)
+    tr = np.trace(np.trace(rho, axis1=0, axis2=1))
+    return rho / tr
+
+
+def reduced_env(B, Ti, Tj, mps_env, aux=None):
+    """(ITE.py:853-1302, mps_env branch)  -> X[Di, Dj, DX], ai[d, D, Di], aj[d, D, Dj], Ti_rest, Tj_rest, w (spectrum of N_red).
+    ``aux`` (dict, optional): receives what ``rho_from_reduced`` needs -- N4 (the environment on the reduced legs, before it is
+    hermitised), the factors a_i, a_j of the ORIGINAL tensors and the two gauge matrices applied to the rest tensors."""
     d, D = Ti.shape[0], Ti.shape[1]
     Di_rest, Dj_rest = Ti.size // (d * D), Tj.size // (d * D)
     n_i, n_j = Ti.ndim - 2, Tj.ndim - 2
@@ -106,6 +124,8 @@ def reduced_env(B, Ti, Tj, mps_env):
     Ni = B.scale(Ni, 1.0 / B.norm(Ni))
     Nj = B.scale(Nj, 1.0 / B.norm(Nj))
     Nred = B.tensordot(Ni, Nj, ([2, 3], [2, 3]))                                       # [Di, Di*, Dj, Dj*]
+    if aux is not None:
+        aux.update(N4=np.asarray(Nred).copy(), ai0=np.asarray(ai).copy(), aj0=np.asarray(aj).copy())
     Nred = B.reshape(B.transpose(Nred, (0, 2, 1, 3)), (Di_red * Dj_red, Di_red * Dj_red))
     Nred = B.hermitize(Nred)
     w, U = B.eigh(Nred)                                                                # ascending
@@ -129,6 +149,8 @@ def reduced_env(B, Ti, Tj, mps_env):
     X = B.transpose(B.tensordot(X, Rj_inv, ([1], [0])), (0, 2, 1))
     Tj_rest = B.transpose(B.tensordot(Tj_rest, Rj_inv, ([0], [0])), (1, 0))
     aj = B.tensordot(aj, Rj, ([2], [1]))
+    if aux is not None:
+        aux.update(Li_inv=np.asarray(Li_inv).copy(), Rj_inv=np.asarray(Rj_inv).copy())
     Di_red, Dj_red = ai.shape[2], aj.shape[2]
     Ti_rest = B.reshape(Ti_rest, (Di_red,) + tuple(Ti.shape[2:]))
     Tj_rest = B.reshape(Tj_rest, (Dj_red,) + tuple(Tj.shape[2:]))
@@ -232,8 +254,11 @@ def ALS_optimization(B, Dmax, exact_ai, exact_aj, X, iter_max=10, eps=1e-6):
     return new_ai, new_aj
 
 
-def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env):
-    """(ITE.py:1761-2020)  -> (Ti_new, Tj_new, spectrum of N_red | None)"""
+def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env, aux=None):
+    """(ITE.py:1761-2020)  -> (Ti_new, Tj_new, spectrum of N_red | None).
+    ``aux`` (dict, optional, not in the reference): when the gate goes through the reduced environment it receives
+    ``rho_before`` and ``rho_after``, the two-site RDMs of (Ti, Tj) and of (Ti_new, Tj_new) in this environment computed from
+    the reduced environment (``rho_from_reduced``) -- what the update loop would otherwise get from two more ``rho_ij`` calls."""
     g = np.asarray(g, dtype=np.complex128)
     gm = g.transpose(0, 2, 1, 3).reshape(g.shape[0] * g.shape[2], g.shape[1] * g.shape[3])
     sc = np.linalg.norm(gm, ord=2)                                    # 4 x 4 host scalar checks, as in the reference
@@ -248,7 +273,8 @@ def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env):
         rescale = g[mi] / (g_i[mi[0], mi[1]] * g_j[mi[2], mi[2]])
         fi = np.sqrt(abs(rescale))
         return (np.asarray(B.tensordot(fi * g_i, Ti, ([1], [0]))), np.asarray(B.tensordot((rescale / fi) * g_j, Tj, ([1], [0]))), None)
-    X, ai, aj, Ti_rest, Tj_rest, w = reduced_env(B, Ti, Tj, mps_env)
+    red = {} if aux is not None else None
+    X, ai, aj, Ti_rest, Tj_rest, w = reduced_env(B, Ti, Tj, mps_env, aux=red)
     d, Di_red, Dj_red = ai.shape[0], ai.shape[2], aj.shape[2]
     ex = B.tensordot(ai, aj, ([1], [1]))                               # [d, Di, d, Dj]
     ex = B.tensordot(g, ex, ([1, 3], [0, 2]))                          # [d, d, Di, Dj]
@@ -261,6 +287,12 @@ def apply_2local_gate(B, g, Dmax, Ti, Tj, mps_env):
     exact_ai = B.transpose(B.reshape(exact_ai, (d, Di_red, Dp)), (0, 2, 1))
     exact_aj = B.transpose(B.reshape(exact_aj, (Dp, d, Dj_red)), (1, 0, 2))
     new_ai, new_aj = ALS_optimization(B, Dmax, exact_ai, exact_aj, X)
+    if aux is not None:
+        # T_i_new = new_ai (Li_inv T_i_rest0), T_j_new = new_aj (T_j_rest0 Rj_inv): the factors on the ORIGINAL rest tensors
+        ai_eff = np.tensordot(np.asarray(new_ai), red["Li_inv"], ([2], [0]))
+        aj_eff = np.tensordot(np.asarray(new_aj), red["Rj_inv"], ([2], [1]))
+        aux["rho_before"] = rho_from_reduced(red["N4"], red["ai0"], red["aj0"])
+        aux["rho_after"] = rho_from_reduced(red["N4"], ai_eff, aj_eff)
     new_Ti = B.tensordot(new_ai, Ti_rest, ([2], [0]))
     new_Tj = B.tensordot(new_aj, Tj_rest, ([2], [0]))
     new_Ti = np.asarray(B.scale(new_Ti, 1.0 / float(np.max(np.abs(np.asarray(new_Ti))))))

@@ -214,13 +214,17 @@ def ite_edge_update(unit_cell: UnitCell, messages: dict | None, N: int, mode: st
     env12 = reduce_to_core(unit_cell, messages, N, chi)
     ti, tj, env, info = edge_tn(unit_cell, env12, N, mode, edge, chi)
     t2 = time.perf_counter()
-    check_rdms_metrics(ite.rho_ij(B, ti, tj, env))                       # _measures_on_edge before the update (_tn_update.py:181)
     d_virtual = ti.shape[1]
-    ti_new, tj_new, origin_eigen_vals = ite.apply_2local_gate(B, g, d_virtual, ti, tj, env)
+    aux = {}
+    ti_new, tj_new, origin_eigen_vals = ite.apply_2local_gate(B, g, d_virtual, ti, tj, env, aux=aux)
+    # _measures_on_edge before and after the update (_tn_update.py:181, 190): both RDMs from the reduced environment the gate
+    # application has built anyway (same contraction as rho_ij, two passes over the ring tensors less); a trivial / product
+    # gate does not build it
+    check_rdms_metrics(aux["rho_before"] if "rho_before" in aux else ite.rho_ij(B, ti, tj, env))
     last = getattr(ite.ALS_optimization, "last", None)
     if last:
         st.als_iterations, st.truncation_distance = last["iterations"], last["distance"]
-    rho = ite.rho_ij(B, ti_new, tj_new, env)
+    rho = aux["rho_after"] if "rho_after" in aux else ite.rho_ij(B, ti_new, tj_new, env)
     energy = float(np.real(np.dot(np.asarray(rho).flatten(), h.flatten())))
     st.env_metrics = check_rdms_metrics(rho)
     st.env_metrics.other["original_negativity_ratio"] = _original_negativity_ratio(origin_eigen_vals)

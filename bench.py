@@ -268,13 +268,17 @@ def run_reference_arm(a, rank):
     T, E, A, K, P = block_tn.assemble(N, cell.tensors(), msgs)
     T, E, A = block_tn.connect_corner(N, T, E, A, P, side)
     order = list(contraction_order.kagome_order(N, side, "ToMessage"))
-    # size the sample: a few minutes for the whole arm
+    # size the sample so that the whole arm ends within a few minutes: the cost per swallow grows along the chain (the bonds
+    # saturate), so the prefix length is found by doubling until one run takes half of the per-step budget
     per_step_budget = max(2.0, 150.0 / max(1, a.steps + a.warmup))
-    k0 = min(len(order), 8 + 2 * L)
-    t0 = time.perf_counter()
-    obub(T, E, A, SIDE_ANGLE[side], order[:k0], D_trunc=chi, ket_tensors=K)
-    t_probe = time.perf_counter() - t0
-    k = min(len(order), max(k0, int(k0 * per_step_budget / t_probe)))
+    k = min(len(order), 8 + 2 * L)
+    while True:
+        t0 = time.perf_counter()
+        obub(T, E, A, SIDE_ANGLE[side], order[:k], D_trunc=chi, ket_tensors=K)
+        t_probe = time.perf_counter() - t0
+        if k >= len(order) or t_probe > per_step_budget / 2:
+            break
+        k = min(len(order), 2 * k)
     times = []
     for i in range(a.warmup + a.steps):
         t0 = time.perf_counter()

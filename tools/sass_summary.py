@@ -11,7 +11,8 @@ txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "kagomeperiodicbp
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 out = ["SASS evidence for libkbp.so (cuobjdump -sass, sm_100a build of this commit; regenerate: tools/sass_summary.py)",
        "mnemonic counts per kernel: DMMA = FP64 tensor core (mma.sync.m16n8k8.f64; tcgen05 has no FP64 kind), LDGSTS = cp.async global->shared,",
-       "STAS / SYNCS / UCGABAR = distributed shared memory stores + mbarrier + cluster barrier, MUFU64 = FP64 rsqrt / reciprocal seeds, SHFL = warp shuffles", ""]
+       "STAS / SYNCS / UCGABAR = distributed shared memory stores + mbarrier + cluster barrier, MUFU64 = FP64 rsqrt / reciprocal seeds, SHFL = warp shuffles,",
+       "UBLKCP = cp.async.bulk (TMA unit, 1-D; the opt-in BULK variants of the small-tile GEMM)", ""]
 rows = []
 for f in funcs:
     name = f.split("\n", 1)[0].strip()
@@ -20,10 +21,10 @@ for f in funcs:
     c2 = collections.Counter(ins)
     dem = re.sub(r"\(.*", "", subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip())
     rows.append((dem, len(ins), c["DMMA"], c["DFMA"] + c["DMUL"] + c["DADD"], c["LDGSTS"], c["LDS"], c["STS"], c["SHFL"], c["BAR"], c["STAS"], c["SYNCS"],
-                 c["UCGABAR"], c2.get("MUFU.RSQ64H", 0) + c2.get("MUFU.RCP64H", 0)))
-out.append(f"{'kernel':78s} {'instr':>6s} {'DMMA':>5s} {'DFP':>5s} {'LDGSTS':>6s} {'LDS':>5s} {'STS':>5s} {'SHFL':>5s} {'BAR':>4s} {'STAS':>4s} {'SYNCS':>5s} {'UCGABAR':>7s} {'MUFU64':>6s}")
+                 c["UCGABAR"], c2.get("MUFU.RSQ64H", 0) + c2.get("MUFU.RCP64H", 0), c["UBLKCP"]))
+out.append(f"{'kernel':78s} {'instr':>6s} {'DMMA':>5s} {'DFP':>5s} {'LDGSTS':>6s} {'LDS':>5s} {'STS':>5s} {'SHFL':>5s} {'BAR':>4s} {'STAS':>4s} {'SYNCS':>5s} {'UCGABAR':>7s} {'MUFU64':>6s} {'UBLKCP':>6s}")
 for r in sorted(rows, key=lambda r: -r[1]):
-    out.append(f"{r[0][:78]:78s} {r[1]:6d} {r[2]:5d} {r[3]:5d} {r[4]:6d} {r[5]:5d} {r[6]:5d} {r[7]:5d} {r[8]:4d} {r[9]:4d} {r[10]:5d} {r[11]:7d} {r[12]:6d}")
+    out.append(f"{r[0][:78]:78s} {r[1]:6d} {r[2]:5d} {r[3]:5d} {r[4]:6d} {r[5]:5d} {r[6]:5d} {r[7]:5d} {r[8]:4d} {r[9]:4d} {r[10]:5d} {r[11]:7d} {r[12]:6d} {r[13]:6d}")
 
 
 def excerpt(pattern, anchor, before, after, title):

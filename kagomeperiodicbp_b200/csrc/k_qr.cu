@@ -162,10 +162,12 @@ void qr_householder(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t wor
 }
 
 bool qr_cholqr2(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);   // k_tsvd.cu
+bool qr_blocked(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);   // k_tsvd.cu
 
 void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
   if (m == 0 || n == 0) return;
   if (qr_cholqr2(a, A, Q, R, work, m, n)) return;          // tall and skinny: Cholesky-QR twice, Householder only if the Gram matrix is too ill conditioned
+  if (qr_blocked(a, A, Q, R, work, m, n)) return;          // large, not skinny: block Gram-Schmidt over tall-skinny blocks
   qr_householder(a, A, Q, R, work, m, n);
 }
 

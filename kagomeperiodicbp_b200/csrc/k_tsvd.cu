@@ -1535,6 +1535,83 @@ bool qr_cholqr2(const Arena& a0, int64_t A, int64_t Q, int64_t R, int64_t work, 
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// QR of a LARGE matrix that is not skinny (m >= n > 96: the 672 x 672 split of the common neighbour in the Mode -> Edge
+// reduction at D = 4, src/tensor_networks/tensor_network.py:1194) by block classical Gram-Schmidt with reorthogonalisation:
+//   for every block of <= 64 columns:  V = A_j - Q_prev (Q_prev^H A_j), twice;  V = Q_j R_jj by the tall-skinny path (Cholesky-QR
+//   twice, Householder per chain if ill conditioned);  R_ij = the two projection coefficients.
+// Everything is GEMMs on the DMMA pipe plus the tall QR kernels: ~3 ms against ~150 ms for the one-CTA Householder kernel,
+// which was 3/4 of the gate update on the edges whose reduction has this split.  Q is kept TRANSPOSED in the workspace
+// (rows = columns of Q, so the blocks found so far are one contiguous matrix for both products).  If any block needed the
+// Householder fallback (rank deficient / ill conditioned input: its Q_j is orthonormal but not guaranteed orthogonal to the
+// earlier blocks) the chain is redone by the Householder kernels, predicated per chain.
+__global__ void qrb_sticky_kernel(double* __restrict__ sticky, const int* __restrict__ state, int nb, int reset) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb) return;
+  if (reset) sticky[c] = 0.0;
+  else if (state[c] == CHAIN_EXACT) sticky[c] = 1.0;
+}
+__global__ void qrb_final_kernel(int* __restrict__ state, const double* __restrict__ sticky, int nb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nb) state[c] = sticky[c] != 0.0 ? CHAIN_EXACT : CHAIN_ACCEPTED;
+}
+// x += y  (n elements)
+__global__ void tsvd_add_kernel(cplx* __restrict__ base, long long chain_stride, long long x_, long long y_, long long n) {
+  cplx* cb = base + (long long)blockIdx.y * chain_stride;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) cb[x_ + e] = cadd(cb[x_ + e], cb[y_ + e]);
+}
+
+void qr(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n);
+
+bool qr_blocked(const Arena& a, int64_t A, int64_t Q, int64_t R, int64_t work, int64_t m, int64_t n) {
+  static const bool on = !(getenv("KBP_QR_BLOCKED") && atoi(getenv("KBP_QR_BLOCKED")) == 0);
+  if (!on || a.mask != nullptr || m < n || n < 128) return false;
+  const int64_t nblocks = (n + 63) / 64;
+  const int64_t w = ((n + nblocks - 1) / nblocks + 7) / 8 * 8;         // block width: <= 64, multiple of 8, no tiny last block
+  const int64_t Qt = work, V = Qt + n * m, Qj = V + m * w, C1 = Qj + m * w, C2 = C1 + n * w, Rjj = C2 + n * w, wk = Rjj + w * w;
+  const int64_t need = (wk - work) + (m * w + m * w + w + 8);
+  if (need > m * n + m * n + n + 8) return false;                       // the op's workspace (kbp_qr_work_elems, k = n)
+  double* sticky = a.svd_off + 5 * a.nb;
+  const int gnb = (a.nb + 127) / 128;
+  qrb_sticky_kernel<<<gnb, 128, 0, a.stream>>>(sticky, a.chain_state, a.nb, 1);
+  ++*a.launches;
+  zero(a, R, n * n);
+  for (int64_t c0 = 0; c0 < n; c0 += w) {
+    const int64_t wj = c0 + w <= n ? w : n - c0, pj = c0;
+    const dim3 gv(grid1d(m * wj), a.nb), gc(grid1d(pj * wj > 0 ? pj * wj : 1), a.nb);
+    tsvd_gather_cols_kernel<<<gv, 256, 0, a.stream>>>(a.base, a.chain_stride, V, A, (int)m, (int)n, (int)c0, (int)wj, nullptr, 0);
+    ++*a.launches;
+    if (pj > 0) {
+      gemm(a, C1, Qt, V, pj, wj, m, OP_J, OP_N);                        // Q_prev^H A_j
+      gemm(a, Qj, Qt, C1, m, wj, pj, OP_T, OP_N);                       // Q_prev (...)
+      tsvd_sub_kernel<<<gv, 256, 0, a.stream>>>(a.base, a.chain_stride, V, Qj, m * wj, nullptr, 0);
+      gemm(a, C2, Qt, V, pj, wj, m, OP_J, OP_N);                        // once more (reorthogonalisation)
+      gemm(a, Qj, Qt, C2, m, wj, pj, OP_T, OP_N);
+      tsvd_sub_kernel<<<gv, 256, 0, a.stream>>>(a.base, a.chain_stride, V, Qj, m * wj, nullptr, 0);
+      tsvd_add_kernel<<<gc, 256, 0, a.stream>>>(a.base, a.chain_stride, C1, C2, pj * wj);
+      tsvd_scatter_cols_kernel<<<gc, 256, 0, a.stream>>>(a.base, a.chain_stride, R, C1, (int)pj, (int)n, (int)c0, (int)wj, nullptr, 0);
+      *a.launches += 4;
+    }
+    qr(a, V, Qj, Rjj, wk, m, wj);                                       // tall and skinny: Cholesky-QR twice (+ per-chain Householder)
+    qrb_sticky_kernel<<<gnb, 128, 0, a.stream>>>(sticky, a.chain_state, a.nb, 0);
+    tsvd_scatter_cols_kernel<<<dim3(grid1d(wj * wj), a.nb), 256, 0, a.stream>>>(a.base, a.chain_stride, R + c0 * n, Rjj, (int)wj, (int)n, (int)c0, (int)wj,
+                                                                                nullptr, 0);
+    *a.launches += 2;
+    const int64_t dims[2] = {m, wj}, perm[2] = {1, 0};
+    permute(a, Qt + c0 * m, Qj, 0, 2, dims, perm);                      // rows [c0, c0 + wj) of Q^T
+  }
+  const int64_t dims[2] = {n, m}, perm[2] = {1, 0};
+  permute(a, Q, Qt, 0, 2, dims, perm);
+  // chains in which some block took the Householder fallback: the whole factorisation again, the stable way
+  qrb_final_kernel<<<gnb, 128, 0, a.stream>>>(a.chain_state, sticky, a.nb);
+  ++*a.launches;
+  Arena body = a;
+  body.mask = a.chain_state;
+  body.mask_want = CHAIN_EXACT;
+  qr_householder(body, A, Q, R, work, m, n);
+  return true;
+}
+
 void init_tsvd_attributes() {
   cudaFuncSetAttribute(cholqr_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 217 * 1024);   // + 8 KB static shared memory <= 227 KB
   cudaFuncSetAttribute(chol_reg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);

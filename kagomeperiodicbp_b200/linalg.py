@@ -9,6 +9,7 @@ There is no CPU fallback: constructing ``DeviceBackend`` without libkbp.so or wi
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -279,7 +280,10 @@ class ResidentBackend:
         return math.exp(v)
 
     def qr(self, m):
-        q, r = self.p.qr(self._dt(m))
+        M = self._dt(m)
+        if os.environ.get("KBP_LINALG_DEBUG"):
+            print(f"[kbp linalg] qr {M.shape}", flush=True)
+        q, r = self.p.qr(M)
         return RArr(self, q), RArr(self, r)
 
     def _svd_raw(self, m):

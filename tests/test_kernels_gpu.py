@@ -70,7 +70,8 @@ def test_tensordot_conj(eng):
 
 @pytest.mark.parametrize("m,n", [(5, 3), (3, 5), (16, 16), (162, 18), (18, 162), (512, 32), (64, 64), (1, 4), (4, 1), (256, 32), (768, 48),
                                  (243, 27), (256, 16), (130, 7), (1024, 40), (1100, 16), (96, 200),
-                                 (1024, 64), (2592, 72), (2000, 40), (1300, 130)])       # last rows: TSQR over row blocks / one-CTA kernel
+                                 (1024, 64), (2592, 72), (2000, 40), (1300, 130),        # TSQR over row blocks / one-CTA kernel
+                                 (672, 672), (300, 200), (700, 129)])                     # large, not skinny: block Gram-Schmidt over tall-skinny blocks
 def test_qr(eng, m, n):
     batch = [[rnd(m, n)] for _ in range(3)]
     # make one of them rank deficient

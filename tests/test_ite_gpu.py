@@ -73,3 +73,22 @@ def test_device_rho_energy_gate_match_reference(B, mode):
         tin, tjn, w = ite.apply_2local_gate(B, g["g"], 2, ti, tj, env)
         assert np.allclose(w, g[f"eig_{key}"], rtol=0, atol=1e-11 * np.max(np.abs(w)))
         assert pair_rel_diff(pair_of(tin, tjn), g[f"pair_{key}"]) < 1e-8, key         # truncation / ALS result to 1e-8
+
+
+def test_device_rho_ij_and_reduced_rdms_against_independent_einsum(B):
+    """D = 4 sized edge (ring bonds of mixed size as the Mode -> Edge reduction makes them, non-Hermitian environment): the device
+    rho_ij and the RDMs the update loop takes from the reduced environment against the independent einsum of oracle/rho_np.py."""
+    from kagomeperiodicbp_b200 import ite
+    from oracle.rho_np import rho_ij_einsum
+    rng = np.random.default_rng(21)
+    rnd = lambda *s: rng.normal(size=s) + 1j * rng.normal(size=s)
+    d, D, bonds = 2, 4, [42, 96, 42, 16, 42, 96]
+    Ti, Tj = rnd(d, D, D, D, D), rnd(d, D, D, D, D)
+    env = [rnd(bonds[k], D, D, bonds[(k + 1) % 6]) / 8 for k in range(6)]
+    ref0 = rho_ij_einsum(Ti, Tj, env)
+    assert np.abs(np.asarray(ite.rho_ij(B, Ti, Tj, env)) - ref0).max() < 1e-11 * np.abs(ref0).max()
+    aux = {}
+    tin, tjn, _ = ite.apply_2local_gate(B, ite.g_from_exp_h(ite.heisenberg_afm(), 1e-2), D, Ti, Tj, env, aux=aux)
+    assert np.abs(aux["rho_before"] - ref0).max() < 1e-10 * np.abs(ref0).max()
+    ref1 = rho_ij_einsum(np.asarray(tin), np.asarray(tjn), env)
+    assert np.abs(aux["rho_after"] - ref1).max() < 1e-9 * np.abs(ref1).max()

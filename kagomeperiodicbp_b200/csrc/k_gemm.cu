@@ -111,8 +111,11 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
   const int gq = lane >> 2, q = lane & 3;
   constexpr bool a_kc = A_KC;                           // A stored [m][k]  (opA == N or J)
   constexpr bool b_kc = B_KC;                           // B stored [n][k]  (opB == T or C)
-  const double sa = (g.opA == OP_C || g.opA == OP_J) ? -1.0 : 1.0;
-  const double sb = (g.opB == OP_C || g.opB == OP_J) ? -1.0 : 1.0;
+  // conjugation = sign flip of the imaginary part, as an integer XOR on the high word (a multiplication by +-1 would be one more
+  // instruction on the FP64 pipe per loaded element, the pipe the DMMAs need)
+  const int sa = (g.opA == OP_C || g.opA == OP_J) ? (int)0x80000000 : 0;
+  const int sb = (g.opB == OP_C || g.opB == OP_J) ? (int)0x80000000 : 0;
+  auto flip = [](double y, int bits) { return __hiloint2double(__double2hiint(y) ^ bits, __double2loint(y)); };
 
   const int slabs_total = (g.k + BK - 1) / BK;
   const int per = (slabs_total + g.ksplit - 1) / g.ksplit;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
         const int mm = wm * 16 + gq + 8 * (v & 1), kk = ks * 8 + q + 4 * (v >> 1);
         const cplx x = a_kc ? at[mm * LDK + kk] : at[kk * LDM + mm];
         ar[v] = x.x;
-        aim[v] = sa * x.y;
+        aim[v] = flip(x.y, sa);
         as[v] = ar[v] + aim[v];
       }
 #pragma unroll
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(32 * NWARPS) zgemm_dmma_kernel(cplx* __restric
           const int kk = ks * 8 + q + 4 * v, nn = wn * (NT * 8) + nt * 8 + gq;
           const cplx x = b_kc ? bt[nn * LDK + kk] : bt[kk * LDN + nn];
           br[v] = x.x;
-          bi[v] = sb * x.y;
+          bi[v] = flip(x.y, sb);
           bs[v] = br[v] + bi[v];
         }
         const int a0 = NACC == 2 ? (ks & 1) : 0;

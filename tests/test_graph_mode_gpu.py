@@ -57,6 +57,8 @@ CASES = {
     "first_check": (512, 512, 32, lambda p: np.sort(np.exp(-0.1 * np.arange(p)) * (1 + 0.3 * rng.random(p)))[::-1]),
     "more_rounds": (512, 512, 32, lambda p: np.exp(-0.02 * np.arange(p))),
     "collapse_exact": (256, 256, 32, lambda p: np.where(np.arange(p) < 20, 1.0, np.where(np.arange(p) < 60, 1e-9, 0.0))),
+    # kept spectrum over more than six decades, but the block resolves a direction below the kept ones: stays on the subspace path
+    "collapse_resolved": (512, 512, 32, lambda p: np.exp(-0.45 * np.arange(p))),
     "reduced_wide": (64, 512, 32, lambda p: np.exp(-0.15 * np.arange(p))),
     "reduced_tall": (512, 64, 32, lambda p: np.exp(-0.15 * np.arange(p))),
     "plain_exact": (200, 160, 150, lambda p: np.exp(-0.05 * np.arange(p))),
@@ -92,6 +94,8 @@ def test_graph_equals_host_driven(engines, name):
         assert d["subspace"] == 3 and d["subspace_iterations"] > 3 * 7, d
     if name == "collapse_exact":
         assert d["subspace_fallback"] == 3 and d["block_jacobi"] == 3 and d["block_jacobi_sweeps"] >= 3, d
+    if name == "collapse_resolved":
+        assert d["subspace"] == 3 and d["subspace_fallback"] == 0 and d["block_jacobi"] == 0, d
     if name.startswith("reduced"):
         assert d["reduced"] == 3 and d["block_jacobi"] == 0, d
     if name == "plain_exact":

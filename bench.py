@@ -75,6 +75,17 @@ def parse():
     return a
 
 
+L2_NOTE = "512 MiB buffer rewritten between timed iterations (L2 flush)"
+SHARDING_CELLS = "independent unit cells per rank, no data-path collective"
+
+
+def config_dict(a, sharding=SHARDING_CELLS, batch=None):
+    """the `config` object of the JSON line -- the same for the GPU arm and for the reference arm of the same invocation"""
+    from kagomeperiodicbp_b200 import contraction_order
+    return {"workload": workload_name(a), "baseline_config": a.config, "unit_cells_per_gpu": a.batch if batch is None else batch, "sharding": sharding,
+            "l2": L2_NOTE, "swallows_per_message": len(contraction_order.kagome_order(a.N, "D", "ToMessage")) - 1}
+
+
 def workload_name(a):
     n_s = 3 * (3 * a.N * a.N - 3 * a.N + 1)
     return (f"Kagome Heisenberg-PEPS block BP, D={a.D}, block N={a.N} ({n_s} sites, 6 messages x {2 * a.N - 1} MPS sites), "
@@ -294,8 +305,7 @@ def run_reference_arm(a, rank):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic", "impl": "reference", "units_per_step": frac,
-            "config": {"workload": workload_name(a), "unit_cells_per_gpu": a.batch,
-                       "sharding": "independent unit cells per rank, no data-path collective", "l2": "n/a (CPU)"},
+            "config": config_dict(a),                      # the GPU arm's config of the same invocation (the L2 note does not apply to the CPU)
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -490,7 +500,7 @@ def main():
     units = 6 * B * world
     value = units / (ms_step * 1e-3)
     e2e_value = units / (ms_e2e * 1e-3)
-    scaling, sharding = "weak", "independent unit cells per rank, no data-path collective"
+    scaling, sharding = "weak", SHARDING_CELLS
     if ms_sharded is not None:
         units, scaling = 6, "strong"
         value = e2e_value = units / (ms_sharded * 1e-3)
@@ -501,9 +511,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "c128",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "baseline_config": a.config, "unit_cells_per_gpu": B, "sharding": sharding,
-                       "l2": "512 MiB buffer rewritten between timed iterations (L2 flush)",
-                       "swallows_per_message": len(bp.contraction_order.kagome_order(N, "D", "ToMessage")) - 1},
+            "config": config_dict(a, sharding, B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ss.h2d), "d2h_bytes_per_step": int(ss.d2h), "ms_per_step": ms_e2e},
             "ms_per_step_by_rank": ms_ranks,
             "gpu_launches": int(n_launch),

@@ -367,6 +367,9 @@ class SideSet:
     def launches(self):
         return sum(self.engs[s].launch_count() for s in self.sides)
 
+    def gemm_flops(self):
+        return sum(self.engs[s].gemm_flops() for s in self.sides)
+
     def graph_counters(self):
         out = {}
         for s in self.sides:
@@ -446,9 +449,10 @@ def main():
     sampler = ClockSampler(dev)
     sampler.start()
     barrier()
-    l0, g0 = ss.launches(), ss.graph_counters()
+    l0, g0, f0 = ss.launches(), ss.graph_counters(), ss.gemm_flops()
     ms_step = timed_steps(ss, a.steps, flush, barrier, torch)
     n_launch = ss.launches() - l0
+    executed_flops = (ss.gemm_flops() - f0) / a.steps
     g1 = ss.graph_counters()
     barrier()
     # ---- end to end through the public API with host buffers
@@ -552,6 +556,12 @@ def main():
                                           "conventions, full-SVD count) / device-timed step / measured FP64 peak: an algorithm-equivalent rate",
                             "peak_source": "cuBLAS DGEMM 4096^3 FP64 measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
                             "algorithmic_flops_per_step": total_flops, "svd_algorithmic_flops_per_step": svd_flops,
+                            "executed_dmma_flops_per_step": executed_flops,
+                            "executed_dmma_tflops": executed_flops / (ms_step * 1e-3) / 1e12,
+                            "executed_dmma_frac_of_peak": executed_flops / (ms_step * 1e-3) / 1e12 / peak,
+                            "executed_note": "real flops the ZGEMM launches of the timed steps executed on the FP64 tensor pipe (6 m n k per complex "
+                                             "product, 3M form; this rank; one-SM kernels -- Cholesky, Jacobi, triangular solve -- not included): the "
+                                             "subspace iteration does a fraction of the flops of the full SVDs the algorithmic count assumes",
                             "svd_paths": paths}
         if world == 1:
             # per-opcode device time of one host-driven, instrumented repetition (events around every op; six streams overlap)

@@ -116,6 +116,10 @@ int64_t kbp_svd_warm_elems(int64_t m, int64_t n, int64_t keep);
 
 /* instrumentation: kernels launched so far; device timing of a region on the context's stream */
 int64_t kbp_launch_count(const kbp_ctx* ctx);
+/* real floating-point operations EXECUTED so far by the ZGEMM launches of this context (6 m n k per complex product: three real
+ * DMMA products, 3M form); launches inside the bodies of conditional graph nodes (rounds beyond the learned schedule) are not
+ * counted.  Against the algorithmic count of the reference's full SVDs this is what the tensor pipe really does. */
+double kbp_gemm_flops(const kbp_ctx* ctx);
 int64_t kbp_svd_sweeps(kbp_ctx* ctx);                 /* total block-Jacobi sweeps + subspace iterations so far (synchronises) */
 /* how the truncations were executed so far (synchronises; [2..7] are counted on the device by the decision kernels):
  * out8[0] Householder reduction + in-shared-memory Jacobi, [1] in-shared-memory Jacobi, [2] accepted from subspace iteration,

@@ -362,6 +362,7 @@ static void launch_gemm(const Arena& a, const GemmArgs& g) {
 
 void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int64_t n, int64_t k, int opA, int opB, int ksplit) {
   if (m == 0 || n == 0) return;
+  if (a.gemm_flops && a.depth == 0) *a.gemm_flops += 6.0 * (double)m * (double)n * (double)k * a.nb;   // (bodies of conditional nodes not counted)
   static const bool ktime = getenv("KBP_KTIME") != nullptr;
   static int kt_next = 0;                                     // (probe runs are single-threaded at capture time)
   GemmArgs g{C, A, B, (int)m, (int)n, (int)k, opA, opB, ksplit < 1 ? 1 : ksplit, 0, 0, a.scratch, a.scratch_stride, a.counters_dev, a.mask, a.mask_want,

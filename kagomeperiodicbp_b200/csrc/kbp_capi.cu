@@ -29,12 +29,13 @@ struct kbp_ctx {
   double* svd_off = nullptr;
   double* svd_off_host = nullptr;
   int64_t launches = 0;
+  double gemm_flops = 0;                 // real flops executed by the ZGEMM launches so far (3M form: 6 m n k each)
   int64_t counters[8] = {0};
   kbp::SvdCtl* ctl = nullptr;            // device control block of the truncation in flight, followed by int state[nb]
   kbp::SvdCtl* ctl_host = nullptr;       // pinned mirror (host-driven mode, counters)
   cudaStream_t body_stream[2] = {nullptr, nullptr};   // capture streams of conditional-node bodies
   // a program can be held as a LIST of graphs launched back to back (KBP_GRAPH_SEGMENT_LAUNCHES; off by default, see kbp_run)
-  struct GraphEntry { cudaGraphExec_t exec = nullptr; std::vector<cudaGraphExec_t> more; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; bool bad = false; bool spec = false; };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; std::vector<cudaGraphExec_t> more; int seen = 0; int64_t launches = 0; int64_t dcount[8] = {0}; double flops = 0; bool bad = false; bool spec = false; };
   std::unordered_map<uint64_t, GraphEntry> graphs;      // CUDA graphs of whole programs, keyed by a hash of the op stream
   std::unordered_map<unsigned long long, int> tsvd_rounds;
   int64_t graph_replays = 0;
@@ -270,6 +271,7 @@ int64_t kbp_qr_work_elems(int64_t m, int64_t n) {
 }
 int64_t kbp_svd_warm_elems(int64_t, int64_t, int64_t) { return 0; }
 int64_t kbp_launch_count(const kbp_ctx* c) { return c ? c->launches : 0; }
+double kbp_gemm_flops(const kbp_ctx* c) { return c ? c->gemm_flops : 0.0; }
 int kbp_svd_counters(kbp_ctx* c, int64_t* out8) {
   if (!c || !out8) return KBP_E_ARG;
   cudaSetDevice(c->device);
@@ -398,18 +400,21 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
     c->last_run_spec = ge.spec;
     c->spec_launches += ge.spec;
     c->launches += ge.launches;
+    c->gemm_flops += ge.flops;
     for (int k = 0; k < 2; ++k) c->counters[k] += ge.dcount[k];
     ++c->graph_replays;
     return KBP_OK;
   }
   if (ge.bad || (ge.seen++ == 0 && !capture_first)) return run_ops(c, w, n_words, false, nullptr, h);
   const int64_t l0 = c->launches;
+  const double f0 = c->gemm_flops;
   int64_t c0[8];
   for (int k = 0; k < 8; ++k) c0[k] = c->counters[k];
   auto give_up = [&](const char* why) {
     ge.bad = true;
     cudaGetLastError();
     c->launches = l0;
+    c->gemm_flops = f0;
     for (int k = 0; k < 8; ++k) c->counters[k] = c0[k];
     fprintf(stderr, "[kbp] graph capture of a %lld-word program failed (%s): running it with host-driven loops\n", (long long)n_words, why);
     return run_ops(c, w, n_words, false, nullptr, h);
@@ -451,6 +456,7 @@ int kbp_run(kbp_ctx* c, const int64_t* w, int64_t n_words) {
   ge.exec = execs[0];
   ge.more.assign(execs.begin() + 1, execs.end());
   ge.launches = c->launches - l0;
+  ge.flops = c->gemm_flops - f0;
   for (int k = 0; k < 8; ++k) ge.dcount[k] = c->counters[k] - c0[k];
   ge.spec = c->speculate;
   ++c->graph_captures;
@@ -522,7 +528,7 @@ static int run_ops(kbp_ctx* c, const int64_t* w, int64_t n_words, bool capture, 
   CU(c, cudaSetDevice(c->device));
   kbp::Arena a;
   a.base = c->arena; a.chain_stride = c->chain_elems; a.slots = c->slots; a.n_slots = c->n_slots; a.nb = c->nb;
-  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.counters = c->counters; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
+  a.stream = c->stream; a.block_event = c->block_event; a.launches = &c->launches; a.gemm_flops = &c->gemm_flops; a.counters = c->counters; a.svd_off = c->svd_off; a.svd_off_host = c->svd_off_host;
   a.scratch = c->scratch; a.scratch_stride = KBP_GEMM_SCRATCH; a.counters_dev = c->counters_dev;
   a.ctl = c->ctl; a.ctl_host = c->ctl_host; a.chain_state = reinterpret_cast<int*>(c->ctl + 1);
   a.mask = nullptr; a.mask_want = 0;

@@ -48,6 +48,7 @@ struct Arena {
   int64_t scratch_stride;
   int* counters_dev;      // split-K tile semaphores: [nb][4096] ints, zero between launches
   int64_t* launches;      // host counter of kernel launches
+  double* gemm_flops;     // host counter (may be null): real flops the ZGEMM launches execute (6 m n k per complex product: 3M form)
   int64_t* counters;      // host counters [8]: see svd_truncate
   SvdCtl* ctl;            // device control block (+ state[nb]) of the truncation in flight, and its pinned host mirror
   SvdCtl* ctl_host;

@@ -19,7 +19,7 @@ E_SVD_NOCONV, E_NONFINITE = -4, -5
 EXPORTED = [
     "kbp_create", "kbp_destroy", "kbp_last_error", "kbp_device_count", "kbp_reserve", "kbp_upload", "kbp_download",
     "kbp_broadcast", "kbp_slots_read", "kbp_slots_zero", "kbp_run", "kbp_sync", "kbp_svd_work_elems",
-    "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
+    "kbp_qr_work_elems", "kbp_svd_warm_elems", "kbp_launch_count", "kbp_gemm_flops", "kbp_svd_sweeps", "kbp_svd_counters", "kbp_timer_start", "kbp_timer_stop_ms",
     "kbp_profile_enable", "kbp_profile_read", "kbp_graph_ready", "kbp_graph_counters", "kbp_graph_policy", "kbp_spec_failed", "kbp_run_relearn", "kbp_set_speculation", "kbp_spec_counters", "kbp_ktime_report", "kbp_arena_ptr", "kbp_slots_ptr", "kbp_stream_ptr", "kbp_chain_elems",
 ]
 
@@ -82,6 +82,7 @@ def load_library():
         lib.kbp_qr_work_elems.argtypes = [L, L]; lib.kbp_qr_work_elems.restype = L
         lib.kbp_svd_warm_elems.argtypes = [L, L, L]; lib.kbp_svd_warm_elems.restype = L
         lib.kbp_launch_count.argtypes = [P]; lib.kbp_launch_count.restype = L
+        lib.kbp_gemm_flops.argtypes = [P]; lib.kbp_gemm_flops.restype = D
         lib.kbp_svd_sweeps.argtypes = [P]; lib.kbp_svd_sweeps.restype = L
         lib.kbp_svd_counters.argtypes = [P, P]; lib.kbp_svd_counters.restype = I
         lib.kbp_timer_start.argtypes = [P]; lib.kbp_timer_start.restype = I
@@ -249,6 +250,10 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.kbp_launch_count(self.h))
+
+    def gemm_flops(self) -> float:
+        """real flops executed so far by the ZGEMM launches of this engine (include/kbp.h: kbp_gemm_flops)."""
+        return float(self.lib.kbp_gemm_flops(self.h))
 
     def svd_sweeps(self) -> int:
         return int(self.lib.kbp_svd_sweeps(self.h))

@@ -81,6 +81,9 @@ class NumpyEngine:
     def sync(self):
         pass
 
+    def gemm_flops(self):
+        return 0.0
+
     def spec_failed(self):
         return False                     # no speculative graphs in the interpreter
 

@@ -389,6 +389,10 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
   // few dozen tiles is bound by the handful of SMs it occupies.  Pick the largest tile that still spreads over the machine.
   const int64_t ctas64 = ((n + 63) / 64) * ((m + 63) / 64) * a.nb * g.ksplit;
   const int64_t ctas32 = ((n + 31) / 32) * ((m + 31) / 32) * a.nb * g.ksplit;
+  const int64_t ctas3264 = ((n + 63) / 64) * ((m + 31) / 32) * a.nb * g.ksplit;
+  // opt-in: measured slower on the 8-cell ensemble (six sides 629 against 601 ms per iteration: 128 CTAs of 8 warps leave each SM
+  // sub-partition two warps, too few to cover the fragment-load latency between the DMMAs)
+  static const bool tile3264 = getenv("KBP_GEMM_TILE3264") && atoi(getenv("KBP_GEMM_TILE3264")) != 0;
   // tuning knobs of the small-product path (tools/gemm_bench.py sweeps them)
   static const int fused_tile = getenv("KBP_GEMM_FUSED_TILE") ? atoi(getenv("KBP_GEMM_FUSED_TILE")) : 16;
   static const int stages16 = getenv("KBP_GEMM_STAGES16") ? atoi(getenv("KBP_GEMM_STAGES16")) : 3;   // measured: 3 stages (30 KB, 7 CTAs per SM) beat 4 on every shape of tools/gemm_bench.py d4
@@ -397,7 +401,8 @@ void gemm_splitk(const Arena& a, int64_t C, int64_t A, int64_t B, int64_t m, int
   else if (stages16 == 3 && (g.fused || ctas32 < 96)) launch_gemm<16, 16, 3, 2>(a, g);
   else if (g.fused) launch_gemm<16, 16, 4, 2>(a, g);
   else if (ctas64 >= 96) launch_gemm<64, 64, 3, 8>(a, g);
-  else if (ctas32 >= 96) launch_gemm<32, 32, 4, 8>(a, g);
+  else if (tile3264 && n >= 64 && ctas3264 >= 96) launch_gemm<32, 64, 3, 8>(a, g);   // batched n = b panels (8 chains x 16 row tiles): two
+  else if (ctas32 >= 96) launch_gemm<32, 32, 4, 8>(a, g);                           // 16 x 8 accumulators per warp share every A fragment
   else launch_gemm<16, 16, 4, 2>(a, g);
 }
 
@@ -432,6 +437,7 @@ void init_gemm_attributes() {
   gemm_attr<16, 16, 3, 2>();
   gemm_attr<16, 16, 2, 2>();
   gemm_attr<32, 32, 4, 8>();
+  gemm_attr<32, 64, 3, 8>();
   gemm_attr<64, 64, 3, 8>();
 }
 
